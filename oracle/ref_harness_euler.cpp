@@ -1,0 +1,59 @@
+// TEST INFRASTRUCTURE ONLY -- never linked, imported or executed by the product path.
+//
+// Headless harness around the UNMODIFIED reference header
+//   /root/reference/eulerian_fluid/src/fluid.h   (class Fluid, lines 19-260)
+// compiled where it lies.  Own translation unit because fluid.h defines global
+// min/max templates (fluid.h:9-17).  Built by oracle/Makefile into
+// oracle/_ref/libref_euler.so (g++ -O2 -std=c++17 -include cstring).
+// new_u/new_v/pressure/new_m are zero-filled after construction (the reference
+// leaves them uninitialised, fluid.h:50-68).
+#include <cstring>
+#include <chrono>
+#include "fluid.h"
+
+extern "C" {
+
+void* refeuler_create(int x, int y, float density, float h) {
+	Fluid* f = new Fluid(x, y, density, h);
+	size_t C = f->getNumCells();
+	std::memset(f->new_u, 0, 4 * C); std::memset(f->new_v, 0, 4 * C);
+	std::memset(f->pressure, 0, 4 * C); std::memset(f->new_m, 0, 4 * C);
+	return f;
+}
+void refeuler_destroy(void* h) { delete (Fluid*)h; }
+void refeuler_dims(void* h, int* ints, float* floats) {
+	Fluid* f = (Fluid*)h;
+	ints[0] = f->getNumX(); ints[1] = f->getNumY(); ints[2] = f->getNumCells();
+	floats[0] = f->density; floats[1] = f->h; floats[2] = f->h1;
+}
+void* refeuler_ptr(void* h, const char* name) {
+	Fluid* f = (Fluid*)h;
+#define FIELD(n) if (!std::strcmp(name, #n)) return (void*)f->n;
+	FIELD(u) FIELD(v) FIELD(new_u) FIELD(new_v) FIELD(pressure) FIELD(solid) FIELD(m) FIELD(new_m)
+#undef FIELD
+	return nullptr;
+}
+void refeuler_solve(void* h, int iters, float dt) { ((Fluid*)h)->solveIncompressibility(iters, dt); }
+void refeuler_extrapolate(void* h) { ((Fluid*)h)->extrapolate(); }
+void refeuler_advect_vel(void* h, float dt) { ((Fluid*)h)->advectVel(dt); }
+void refeuler_advect_smoke(void* h, float dt) { ((Fluid*)h)->advectSmoke(dt); }
+float refeuler_sample(void* h, float x, float y, int field) { return ((Fluid*)h)->sampleField(x, y, field); }
+// caller sequence of eulerian_fluid/src/fluid_ui.h:107-111
+void refeuler_step(void* h, int iters, float dt, int n_steps, double* phase_ns) {
+	Fluid* f = (Fluid*)h;
+	using clk = std::chrono::steady_clock;
+	for (int k = 0; k < n_steps; k++) {
+		auto t0 = clk::now();
+		f->solveIncompressibility(iters, dt);
+		auto t1 = clk::now();
+		f->extrapolate();
+		f->advectVel(dt);
+		f->advectSmoke(dt);
+		auto t2 = clk::now();
+		if (phase_ns) {
+			phase_ns[0] += std::chrono::duration<double, std::nano>(t1 - t0).count();
+			phase_ns[1] += std::chrono::duration<double, std::nano>(t2 - t1).count();
+		}
+	}
+}
+}
