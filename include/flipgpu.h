@@ -1,0 +1,170 @@
+/* flipgpu.h -- C ABI of the B200-native grid-fluid step (libflipgpu.so).
+ *
+ * Drop-in boundary for ONE hot path of owenbharrison/simsAndGames: the per-sim
+ * state + step surface that the reference UI shells touch,
+ *   struct FlipFluid   flip_fluid/src/flip_fluid.h:13-582   (caller: flip_fluid/src/main.cpp:32-168)
+ *   class  Fluid       eulerian_fluid/src/fluid.h:19-260     (caller: eulerian_fluid/src/fluid_ui.h:64-111)
+ * The reference has no FFI of its own; these entry points are what a
+ * binding for that surface needs: create / upload / step / readback / destroy.
+ *
+ * Conventions
+ *  - plain C, opaque handles, host pointers + element counts, no torch/CUDA types.
+ *  - every call returns 0 on success, a FLIPGPU_E* code otherwise;
+ *    flipgpu_last_error() gives the message (thread-local).
+ *  - a handle is not thread-safe (the reference is single-threaded).
+ *  - arrays cross the boundary in the REFERENCE layout and index order:
+ *    FLIP grid x-fastest  fIX(i,j)=i+f_num_x*j (flip_fluid.h:147-149), particles AoS xy / rgb
+ *    in the caller's particle index order; Eulerian grid y-fastest ix(i,j)=i*num_y+j (fluid.h:94-96).
+ *  - undefined reference state (flip_fluid.h:76-110 never initialises its arrays) is
+ *    defined as all-zero here (particle colour blue = 1 as flip_fluid.h:94-96).
+ *  - there is no CPU fallback: without a CUDA device every create call fails.
+ */
+#ifndef FLIPGPU_H
+#define FLIPGPU_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLIPGPU_OK 0
+#define FLIPGPU_EINVAL 1   /* bad argument / bad handle / count mismatch */
+#define FLIPGPU_ECUDA 2    /* a CUDA runtime call failed */
+#define FLIPGPU_ENODEV 3   /* no usable CUDA device (no CPU fallback exists) */
+#define FLIPGPU_ENCCL 4    /* an NCCL call failed */
+#define FLIPGPU_ESTATE 5   /* call not valid in this state (e.g. sharded-only call on a 1-GPU handle) */
+
+const char* flipgpu_last_error(void);
+int flipgpu_version(void);
+int flipgpu_device_count(int* count);
+
+/* ------------------------------------------------------------------ FLIP (flip_fluid.h) */
+typedef struct FlipSim FlipSim;
+
+/* constructor arguments, FlipFluid(d,width,height,sp,r,m) flip_fluid.h:62-65 */
+typedef struct {
+	float density, width, height, spacing, particle_radius;
+	int max_particles;
+	int device; /* CUDA ordinal; -1 = current device */
+} FlipParams;
+
+/* derived sizes, computed on the host in fp32 exactly as flip_fluid.h:69-74,103-106 */
+typedef struct {
+	int f_num_x, f_num_y, f_num_cells;
+	int p_num_x, p_num_y, p_num_cells;
+	int max_particles, num_particles;
+	float density, h, f_inv_spacing, particle_radius, p_inv_spacing;
+} FlipDims;
+
+/* state arrays of struct FlipFluid (flip_fluid.h:23-55), addressable for upload/readback */
+typedef enum {
+	FLIP_U = 0, FLIP_V, FLIP_DU, FLIP_DV, FLIP_PREV_U, FLIP_PREV_V, FLIP_P, FLIP_S, /* float[C] */
+	FLIP_CELL_TYPE,          /* int[C]: 0 fluid, 1 air, 2 solid (flip_fluid.h:30-34) */
+	FLIP_CELL_COLOR,         /* float[3C] */
+	FLIP_PARTICLE_POS,       /* float[2*num_particles] */
+	FLIP_PARTICLE_VEL,       /* float[2*num_particles] */
+	FLIP_PARTICLE_COLOR,     /* float[3*num_particles] */
+	FLIP_PARTICLE_DENSITY,   /* float[C] */
+	FLIP_NUM_CELL_PARTICLES, /* int[p_num_cells] */
+	FLIP_FIRST_CELL_PARTICLE,/* int[p_num_cells+1] */
+	FLIP_CELL_PARTICLE_IDS,  /* int[num_particles] */
+	FLIP_FIELD_COUNT
+} FlipField;
+
+typedef enum {
+	FLIP_SOLVER_RED_BLACK = 0,     /* performance order (north_star); bounded against the reference order */
+	FLIP_SOLVER_LEX_WAVEFRONT = 1  /* anti-diagonal schedule, bit-identical to the loop order of flip_fluid.h:458-494 */
+} FlipSolverOrder;
+
+/* the 13 arguments of FlipFluid::simulate (flip_fluid.h:560-565) + two switches */
+typedef struct {
+	float dt, gravity, flip_ratio;
+	int num_pressure_iters, num_particle_iters;
+	float over_relaxation;
+	int compensate_drift, separate_particles;
+	float obstacle_x, obstacle_y, obstacle_vel_x, obstacle_vel_y, obstacle_radius;
+	int solver_order;   /* FlipSolverOrder */
+	int update_colors;  /* run updateParticleColors/updateCellColors + colour diffusion (flip_fluid.h:239-245,498-557) */
+} FlipStepParams;
+
+typedef enum {
+	FLIP_SCALAR_REST_DENSITY = 0, /* particle_rest_density (flip_fluid.h:44,321-332) */
+	FLIP_SCALAR_RESIDUAL_MAX,     /* max |div| over cells the solver updates, incl. drift term */
+	FLIP_SCALAR_RESIDUAL_RMS,
+	FLIP_SCALAR_MAX_PUSH          /* largest particle displacement since the last binning, in hash cells */
+} FlipScalar;
+
+/* phases of simulate() for flip_get_timings, ms accumulated since flip_reset_timings */
+enum { FLIP_PH_INTEGRATE_BIN = 0, FLIP_PH_SEPARATE, FLIP_PH_COLLIDE_MARK, FLIP_PH_P2G, FLIP_PH_SOLVE,
+       FLIP_PH_G2P, FLIP_PH_COLORS, FLIP_PH_COUNT };
+
+int flip_create(const FlipParams* params, FlipSim** out);
+int flip_destroy(FlipSim* sim);
+int flip_get_dims(FlipSim* sim, FlipDims* dims);
+/* num_particles is a public member the caller sets (flip_fluid/src/main.cpp:59) */
+int flip_set_num_particles(FlipSim* sim, int n);
+/* host -> device, reference layout; count = number of elements (not bytes) and must match the field */
+int flip_upload(FlipSim* sim, int field, const void* host, size_t count);
+/* device -> host, reference layout and particle index order */
+int flip_readback(FlipSim* sim, int field, void* host, size_t count);
+/* device equivalent of FluidUI::setObstacle (flip_fluid/src/main.cpp:95-126): rewrites s (and u,v inside
+ * the disc) over 1<=i<nx-2, 1<=j<ny-2 (Q10) with the given obstacle velocity */
+int flip_set_obstacle(FlipSim* sim, float x, float y, float vx, float vy, float radius);
+/* n_steps x FlipFluid::simulate (flip_fluid.h:560-581); asynchronous on the handle's stream */
+int flip_step(FlipSim* sim, const FlipStepParams* sp, int n_steps);
+/* single phases, for same-state replay tests (each cites its reference lines in flipgpu.cu) */
+int flip_phase_integrate(FlipSim* sim, float dt, float gravity);                    /* :156-162 */
+int flip_phase_bin(FlipSim* sim);                                                    /* :169-198 */
+int flip_phase_separate(FlipSim* sim, int num_iters, int update_colors);             /* :201-250, parallel schedule */
+int flip_phase_collide(FlipSim* sim, float ox, float oy, float ovx, float ovy, float orad); /* :254-289 */
+int flip_phase_p2g(FlipSim* sim);                                                    /* :339-403,432-446 + :292-333 */
+int flip_phase_solve(FlipSim* sim, int iters, float dt, float omega, int drift, int order); /* :451-495 */
+int flip_phase_g2p(FlipSim* sim, float flip_ratio);                                  /* :404-429 */
+int flip_phase_colors(FlipSim* sim);                                                 /* :498-557 */
+int flip_get_scalar(FlipSim* sim, int which, float* out);
+int flip_set_rest_density(FlipSim* sim, float rest);
+int flip_synchronize(FlipSim* sim);
+/* the CUDA stream all work of this handle is issued on (a cudaStream_t), for event timing by the caller */
+int flip_get_stream(FlipSim* sim, void** stream);
+int flip_get_timings(FlipSim* sim, float* ms, int count);
+int flip_reset_timings(FlipSim* sim);
+int flip_enable_timings(FlipSim* sim, int on);
+/* kernels launched by this handle since creation (all hand-written sm_100a kernels of this library) */
+int flip_get_launch_count(FlipSim* sim, long long* launches);
+
+/* scene helper = the particle lattice + tank walls of flip_fluid/src/main.cpp:47-77 written into host
+ * buffers (pos: 2*max floats, s: nx*ny floats); returns the particle count through *num_particles.
+ * Pass pos==NULL to only query the count. */
+int flip_scene_tank(float tank_width, float tank_height, float spacing, float radius, float rel_w, float rel_h,
+                    int f_num_x, int f_num_y, float* pos, size_t pos_capacity, float* s, int* num_particles);
+
+/* ------------------------------------------------------------------ Eulerian (fluid.h) */
+typedef struct EulerSim EulerSim;
+typedef enum {
+	EULER_U = 0, EULER_V, EULER_NEW_U, EULER_NEW_V, EULER_PRESSURE, EULER_M, EULER_NEW_M, /* float[C] */
+	EULER_SOLID,  /* unsigned char[C] (the reference's bool[]) */
+	EULER_FIELD_COUNT
+} EulerField;
+typedef struct { int num_x, num_y, num_cells; float density, h, h1; } EulerDims;
+
+int euler_create(int x, int y, float density, float h, int device, EulerSim** out);  /* Fluid(x,y,d,h) fluid.h:41 */
+int euler_destroy(EulerSim* sim);
+int euler_get_dims(EulerSim* sim, EulerDims* dims);
+int euler_upload(EulerSim* sim, int field, const void* host, size_t count);
+int euler_readback(EulerSim* sim, int field, void* host, size_t count);
+int euler_project(EulerSim* sim, int iters, float dt, int order);  /* solveIncompressibility fluid.h:98-139 */
+int euler_extrapolate(EulerSim* sim);                              /* fluid.h:142-151 */
+int euler_advect_vel(EulerSim* sim, float dt);                     /* fluid.h:210-239 */
+int euler_advect_smoke(EulerSim* sim, float dt);                   /* fluid.h:241-259 */
+/* n_steps x (project, extrapolate, advectVel, advectSmoke) = eulerian_fluid/src/fluid_ui.h:107-111 */
+int euler_step(EulerSim* sim, int iters, float dt, int order, int n_steps);
+/* sampleField fluid.h:153-188 at n query points (field: 0 U, 1 V, 2 S) */
+int euler_sample_field(EulerSim* sim, int field, const float* xs, const float* ys, float* out, size_t n);
+int euler_get_residual(EulerSim* sim, float* max_div, float* rms_div);
+int euler_synchronize(EulerSim* sim);
+int euler_get_stream(EulerSim* sim, void** stream);
+int euler_get_launch_count(EulerSim* sim, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

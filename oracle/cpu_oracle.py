@@ -119,6 +119,21 @@ class FlipOracle:
     def push_apart(self, iters):
         fn = self._fn("push_apart"); fn.argtypes = [C.c_void_p, C.c_int]; fn(self.h_, iters)
 
+    def bin_particles(self):
+        """binning half of pushParticlesApart only (flip_fluid.h:169-198); port back-end only."""
+        assert self.kind == "port", "the reference has no separate binning entry point"
+        fn = self._fn("bin"); fn.argtypes = [C.c_void_p]; fn(self.h_)
+
+    def separate(self, iters):
+        """the serial sweeps of flip_fluid.h:201-250 on the existing bins; port back-end only."""
+        assert self.kind == "port"
+        fn = self._fn("separate"); fn.argtypes = [C.c_void_p, C.c_int]; fn(self.h_, iters)
+
+    def separate_jacobi(self, iters, with_colors=False):
+        """CPU model of the product's parallel separation schedule (NOT the reference's order)."""
+        assert self.kind == "port"
+        fn = self._fn("separate_jacobi"); fn.argtypes = [C.c_void_p, C.c_int, C.c_int]; fn(self.h_, iters, int(with_colors))
+
     def collide(self, ox, oy, ovx, ovy, orad):
         fn = self._fn("collide"); fn.argtypes = [C.c_void_p] + [C.c_float] * 5; fn(self.h_, ox, oy, ovx, ovy, orad)
 

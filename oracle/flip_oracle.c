@@ -420,3 +420,56 @@ void orcflip_simulate(void* h, float dt, float gravity, float flip_ratio, int nu
 	orcflip_simulate_timed(h, dt, gravity, flip_ratio, num_pressure_iters, num_particle_iters, over_relaxation,
 	                       compensate_drift, separate_particles, ox, oy, ovx, ovy, orad, n_steps, NULL);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * CPU model of the PRODUCT's parallel separation schedule (not in the reference).
+ * The reference sweep (orcflip_separate above, flip_fluid.h:201-250) is a serial Gauss-Seidel with
+ * an asymmetric pair update and has no parallel equivalent; the CUDA kernel k_separate runs one
+ * Jacobi sweep per launch instead.  This function is that schedule restated on the CPU so the
+ * kernel can be checked BIT-EXACTLY against it, and so its statistical distance to the reference
+ * sweep can be measured on the CPU (tests/test_separation_model.py):
+ *   for every particle i, from the positions at the start of the sweep: window from the current
+ *   position (:208-213), rows yi ascending, slots of the row segment ascending (= pIX order,
+ *   descending id inside a cell), symmetric half-overlap push of :231-235 applied to i only.
+ * Requires the bins of orcflip_bin (built once before the first sweep, Q6). */
+void orcflip_separate_jacobi(void* h, int num_iter, int with_colors) {
+	Flip* f = (Flip*)h;
+	float min_dist = 2 * f->radius, min_dist_sq = min_dist * min_dist;
+	size_t n2 = 2 * (size_t)f->np, n3 = 3 * (size_t)f->np;
+	float* next = malloc(4 * (n2 ? n2 : 1));
+	float* ncol = malloc(4 * (n3 ? n3 : 1));
+	for (int it = 0; it < num_iter; it++) {
+		const float* pos = f->ppos;
+		for (int i = 0; i < f->np; i++) {
+			float px = pos[2 * i], py = pos[2 * i + 1];
+			float ax = px, ay = py;
+			float c0 = f->pcol[3 * i], c1 = f->pcol[3 * i + 1], c2 = f->pcol[3 * i + 2];
+			int pxi = (int)(px * f->p_inv), pyi = (int)(py * f->p_inv);
+			int x0 = maxi(pxi - 1, 0), y0 = maxi(pyi - 1, 0);
+			int x1 = mini(pxi + 1, f->pnx - 1), y1 = mini(pyi + 1, f->pny - 1);
+			if (x0 <= x1)
+				for (int yi = y0; yi <= y1; yi++)
+					for (int k = f->fcp[x0 + f->pnx * yi]; k < f->fcp[x1 + f->pnx * yi + 1]; k++) {
+						int q = f->ids[k];
+						if (q == i) continue;
+						float dx = pos[2 * q] - px, dy = pos[2 * q + 1] - py;
+						float d2 = dx * dx + dy * dy;
+						if (d2 > min_dist_sq || d2 == 0) continue;
+						float d = sqrtf(d2);
+						float sc = .5f * (min_dist - d) / d;
+						ax -= dx * sc;
+						ay -= dy * sc;
+						if (with_colors) {
+							c0 += .001f * ((c0 + f->pcol[3 * q]) / 2.f - c0);
+							c1 += .001f * ((c1 + f->pcol[3 * q + 1]) / 2.f - c1);
+							c2 += .001f * ((c2 + f->pcol[3 * q + 2]) / 2.f - c2);
+						}
+					}
+			next[2 * i] = ax; next[2 * i + 1] = ay;
+			ncol[3 * i] = c0; ncol[3 * i + 1] = c1; ncol[3 * i + 2] = c2;
+		}
+		memcpy(f->ppos, next, 4 * n2);
+		if (with_colors) memcpy(f->pcol, ncol, 4 * n3);
+	}
+	free(next); free(ncol);
+}

@@ -1,0 +1,364 @@
+"""ctypes binding of libflipgpu.so (include/flipgpu.h) with the reference's member names.
+
+FlipFluidGPU mirrors struct FlipFluid (reference flip_fluid/src/flip_fluid.h:13-582):
+same constructor arguments (:62-65), same simulate() signature (:560-565), same public
+scalars (f_num_x, h, particle_radius, num_particles, ...), and fIX/pIX.  The public raw arrays
+of the reference (u, v, s, particle_pos, ...) live in HBM here, so they are exchanged with
+`upload(name, array)` / `readback(name)` in the reference's layout and index order.
+FluidGPU mirrors class Fluid (reference eulerian_fluid/src/fluid.h:19-260).
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+RED_BLACK = 0
+LEX_WAVEFRONT = 1
+
+FLIP_FIELDS = {  # name -> (enum value, numpy dtype)   order == FlipField in flipgpu.h
+    "u": (0, np.float32), "v": (1, np.float32), "du": (2, np.float32), "dv": (3, np.float32),
+    "prev_u": (4, np.float32), "prev_v": (5, np.float32), "p": (6, np.float32), "s": (7, np.float32),
+    "cell_type": (8, np.int32), "cell_color": (9, np.float32),
+    "particle_pos": (10, np.float32), "particle_vel": (11, np.float32), "particle_color": (12, np.float32),
+    "particle_density": (13, np.float32),
+    "num_cell_particles": (14, np.int32), "first_cell_particle": (15, np.int32), "cell_particle_ids": (16, np.int32),
+}
+EULER_FIELDS = {"u": (0, np.float32), "v": (1, np.float32), "new_u": (2, np.float32), "new_v": (3, np.float32),
+                "pressure": (4, np.float32), "m": (5, np.float32), "new_m": (6, np.float32), "solid": (7, np.uint8)}
+FLIP_PHASES = ["integrate_bin", "separate", "collide_mark", "p2g", "solve", "g2p", "colors"]
+
+
+class FlipGpuError(RuntimeError):
+    pass
+
+
+class _FlipParams(C.Structure):
+    _fields_ = [("density", C.c_float), ("width", C.c_float), ("height", C.c_float), ("spacing", C.c_float),
+                ("particle_radius", C.c_float), ("max_particles", C.c_int), ("device", C.c_int)]
+
+
+class _FlipDims(C.Structure):
+    _fields_ = [("f_num_x", C.c_int), ("f_num_y", C.c_int), ("f_num_cells", C.c_int),
+                ("p_num_x", C.c_int), ("p_num_y", C.c_int), ("p_num_cells", C.c_int),
+                ("max_particles", C.c_int), ("num_particles", C.c_int),
+                ("density", C.c_float), ("h", C.c_float), ("f_inv_spacing", C.c_float),
+                ("particle_radius", C.c_float), ("p_inv_spacing", C.c_float)]
+
+
+class _FlipStepParams(C.Structure):
+    _fields_ = [("dt", C.c_float), ("gravity", C.c_float), ("flip_ratio", C.c_float),
+                ("num_pressure_iters", C.c_int), ("num_particle_iters", C.c_int),
+                ("over_relaxation", C.c_float), ("compensate_drift", C.c_int), ("separate_particles", C.c_int),
+                ("obstacle_x", C.c_float), ("obstacle_y", C.c_float), ("obstacle_vel_x", C.c_float),
+                ("obstacle_vel_y", C.c_float), ("obstacle_radius", C.c_float),
+                ("solver_order", C.c_int), ("update_colors", C.c_int)]
+
+
+class _EulerDims(C.Structure):
+    _fields_ = [("num_x", C.c_int), ("num_y", C.c_int), ("num_cells", C.c_int),
+                ("density", C.c_float), ("h", C.c_float), ("h1", C.c_float)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libflipgpu.so")
+
+
+def build_library(verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> simsandgames_b200/libflipgpu.so (in-tree)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise FlipGpuError("building libflipgpu.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+
+
+def load_library():
+    """Load the C-ABI library.  Raises if it has not been built: there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise FlipGpuError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(simsandgames_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.flipgpu_last_error.restype = C.c_char_p
+    _LIB = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().flipgpu_last_error().decode(errors="replace")
+        raise FlipGpuError(f"{what} failed (code {rc}): {msg}")
+
+
+def _as_c(arr, dtype):
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+class FlipFluidGPU:
+    """FlipFluid(d, width, height, sp, r, m) -- flip_fluid.h:62-65 -- with its state in B200 HBM."""
+
+    def __init__(self, density, width, height, spacing, particle_radius, max_particles, device=-1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        pr = _FlipParams(density, width, height, spacing, particle_radius, max_particles, device)
+        _check(self._lib.flip_create(C.byref(pr), C.byref(self._h)), "flip_create")
+        self._refresh()
+
+    def _refresh(self):
+        d = _FlipDims()
+        _check(self._lib.flip_get_dims(self._h, C.byref(d)), "flip_get_dims")
+        for name, _ in _FlipDims._fields_:
+            v = getattr(d, name)
+            setattr(self, "_" + name if name == "num_particles" else name, np.float32(v) if isinstance(v, float) else v)
+
+    # ---- reference members
+    @property
+    def num_particles(self):
+        return self._num_particles
+
+    @num_particles.setter
+    def num_particles(self, n):  # flip_fluid/src/main.cpp:59 writes this member directly
+        _check(self._lib.flip_set_num_particles(self._h, int(n)), "flip_set_num_particles")
+        self._num_particles = int(n)
+
+    @property
+    def particle_rest_density(self):
+        out = C.c_float()
+        _check(self._lib.flip_get_scalar(self._h, 0, C.byref(out)), "flip_get_scalar")
+        return np.float32(out.value)
+
+    @particle_rest_density.setter
+    def particle_rest_density(self, v):
+        _check(self._lib.flip_set_rest_density(self._h, C.c_float(v)), "flip_set_rest_density")
+
+    def fIX(self, i, j):  # flip_fluid.h:147-149
+        return i + self.f_num_x * j
+
+    def pIX(self, i, j):  # flip_fluid.h:151-153
+        return i + self.p_num_x * j
+
+    def _count(self, name):
+        Cn, P, H = self.f_num_cells, self._num_particles, self.p_num_cells
+        return {"cell_color": 3 * Cn, "particle_pos": 2 * P, "particle_vel": 2 * P, "particle_color": 3 * P,
+                "num_cell_particles": H, "first_cell_particle": H + 1, "cell_particle_ids": P}.get(name, Cn)
+
+    def upload(self, name, array):
+        fid, dt = FLIP_FIELDS[name]
+        a, p = _as_c(np.asarray(array).reshape(-1), dt)
+        _check(self._lib.flip_upload(self._h, fid, p, C.c_size_t(a.size)), f"flip_upload({name})")
+
+    def readback(self, name, out=None):
+        fid, dt = FLIP_FIELDS[name]
+        n = self._count(name)
+        if out is None:
+            out = np.empty(n, dt)
+        _check(self._lib.flip_readback(self._h, fid, out.ctypes.data_as(C.c_void_p), C.c_size_t(n)), f"flip_readback({name})")
+        return out
+
+    def readback_into(self, name, ptr, count):
+        """readback into a raw host pointer (e.g. pinned torch memory)."""
+        fid, _ = FLIP_FIELDS[name]
+        _check(self._lib.flip_readback(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"flip_readback({name})")
+
+    def upload_from(self, name, ptr, count):
+        fid, _ = FLIP_FIELDS[name]
+        _check(self._lib.flip_upload(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"flip_upload({name})")
+
+    def set_obstacle(self, x, y, vx=0.0, vy=0.0, radius=0.15):
+        """device equivalent of FluidUI::setObstacle, flip_fluid/src/main.cpp:95-126"""
+        _check(self._lib.flip_set_obstacle(self._h, *[C.c_float(t) for t in (x, y, vx, vy, radius)]), "flip_set_obstacle")
+
+    def simulate(self, dt, gravity, flip_ratio, num_pressure_iters, num_particle_iters, over_relaxation,
+                 compensate_drift, separate_particles, obstacle_x, obstacle_y, obstacle_vel_x, obstacle_vel_y,
+                 obstacle_radius, n_steps=1, solver_order=RED_BLACK, update_colors=True):
+        """FlipFluid::simulate, flip_fluid.h:560-565 (the first 13 arguments are the reference's)."""
+        sp = _FlipStepParams(dt, gravity, flip_ratio, num_pressure_iters, num_particle_iters, over_relaxation,
+                             int(compensate_drift), int(separate_particles), obstacle_x, obstacle_y,
+                             obstacle_vel_x, obstacle_vel_y, obstacle_radius, solver_order, int(update_colors))
+        _check(self._lib.flip_step(self._h, C.byref(sp), int(n_steps)), "flip_step")
+
+    # ---- single phases (same-state replay)
+    def integrateParticles(self, dt, gravity):
+        _check(self._lib.flip_phase_integrate(self._h, C.c_float(dt), C.c_float(gravity)), "flip_phase_integrate")
+
+    def binParticles(self):
+        _check(self._lib.flip_phase_bin(self._h), "flip_phase_bin")
+
+    def separateParticles(self, num_iter, update_colors=False):
+        _check(self._lib.flip_phase_separate(self._h, int(num_iter), int(update_colors)), "flip_phase_separate")
+
+    def pushParticlesApart(self, num_iter, update_colors=False):  # flip_fluid.h:165-251 = bin + sweeps
+        self.binParticles()
+        self.separateParticles(num_iter, update_colors)
+
+    def handleParticleCollisions(self, ox, oy, ovx, ovy, orad):
+        _check(self._lib.flip_phase_collide(self._h, *[C.c_float(t) for t in (ox, oy, ovx, ovy, orad)]), "flip_phase_collide")
+
+    def transferVelocitiesToGrid(self):  # transferVelocities(true) + updateParticleDensity
+        _check(self._lib.flip_phase_p2g(self._h), "flip_phase_p2g")
+
+    def solveIncompressibility(self, num_iters, dt, over_relaxation, compensate_drift=True, solver_order=RED_BLACK):
+        _check(self._lib.flip_phase_solve(self._h, int(num_iters), C.c_float(dt), C.c_float(over_relaxation),
+                                          int(compensate_drift), int(solver_order)), "flip_phase_solve")
+
+    def transferVelocitiesToParticles(self, flip_ratio):
+        _check(self._lib.flip_phase_g2p(self._h, C.c_float(flip_ratio)), "flip_phase_g2p")
+
+    def updateColors(self):
+        _check(self._lib.flip_phase_colors(self._h), "flip_phase_colors")
+
+    # ---- diagnostics
+    def residual(self):
+        mx, rms = C.c_float(), C.c_float()
+        _check(self._lib.flip_get_scalar(self._h, 1, C.byref(mx)), "flip_get_scalar")
+        _check(self._lib.flip_get_scalar(self._h, 2, C.byref(rms)), "flip_get_scalar")
+        return float(mx.value), float(rms.value)
+
+    def max_push_cells(self):
+        out = C.c_float()
+        _check(self._lib.flip_get_scalar(self._h, 3, C.byref(out)), "flip_get_scalar")
+        return int(out.value)
+
+    def synchronize(self):
+        _check(self._lib.flip_synchronize(self._h), "flip_synchronize")
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        _check(self._lib.flip_get_stream(self._h, C.byref(s)), "flip_get_stream")
+        return s.value or 0
+
+    def enable_timings(self, on=True):
+        _check(self._lib.flip_enable_timings(self._h, int(on)), "flip_enable_timings")
+
+    def reset_timings(self):
+        _check(self._lib.flip_reset_timings(self._h), "flip_reset_timings")
+
+    def timings(self):
+        ms = (C.c_float * len(FLIP_PHASES))()
+        _check(self._lib.flip_get_timings(self._h, ms, len(FLIP_PHASES)), "flip_get_timings")
+        return dict(zip(FLIP_PHASES, list(ms)))
+
+    @property
+    def launch_count(self):
+        n = C.c_longlong()
+        _check(self._lib.flip_get_launch_count(self._h, C.byref(n)), "flip_get_launch_count")
+        return n.value
+
+    def close(self):
+        if self._h:
+            self._lib.flip_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FluidGPU:
+    """Fluid(x, y, d, h) -- eulerian_fluid/src/fluid.h:41 -- with its state in B200 HBM (y-fastest arrays)."""
+    U_FIELD, V_FIELD, S_FIELD = 0, 1, 2  # fluid.h:33-37
+
+    def __init__(self, x, y, density, h, device=-1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.euler_create(int(x), int(y), C.c_float(density), C.c_float(h), int(device), C.byref(self._h)),
+               "euler_create")
+        d = _EulerDims()
+        _check(self._lib.euler_get_dims(self._h, C.byref(d)), "euler_get_dims")
+        self._num_x, self._num_y, self._num_cells = d.num_x, d.num_y, d.num_cells
+        self.density, self.h, self.h1 = np.float32(d.density), np.float32(d.h), np.float32(d.h1)
+
+    def getNumX(self):
+        return self._num_x
+
+    def getNumY(self):
+        return self._num_y
+
+    def getNumCells(self):
+        return self._num_cells
+
+    def ix(self, i, j):  # fluid.h:94-96
+        return i * self._num_y + j
+
+    def upload(self, name, array):
+        fid, dt = EULER_FIELDS[name]
+        a, p = _as_c(np.asarray(array).reshape(-1), dt)
+        _check(self._lib.euler_upload(self._h, fid, p, C.c_size_t(a.size)), f"euler_upload({name})")
+
+    def readback(self, name):
+        fid, dt = EULER_FIELDS[name]
+        out = np.empty(self._num_cells, dt)
+        _check(self._lib.euler_readback(self._h, fid, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)), f"euler_readback({name})")
+        return out.reshape(self._num_x, self._num_y)
+
+    def readback_into(self, name, ptr, count):
+        fid, _ = EULER_FIELDS[name]
+        _check(self._lib.euler_readback(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"euler_readback({name})")
+
+    def upload_from(self, name, ptr, count):
+        fid, _ = EULER_FIELDS[name]
+        _check(self._lib.euler_upload(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"euler_upload({name})")
+
+    def solveIncompressibility(self, num_iter, dt, solver_order=RED_BLACK):
+        _check(self._lib.euler_project(self._h, int(num_iter), C.c_float(dt), int(solver_order)), "euler_project")
+
+    def extrapolate(self):
+        _check(self._lib.euler_extrapolate(self._h), "euler_extrapolate")
+
+    def advectVel(self, dt):
+        _check(self._lib.euler_advect_vel(self._h, C.c_float(dt)), "euler_advect_vel")
+
+    def advectSmoke(self, dt):
+        _check(self._lib.euler_advect_smoke(self._h, C.c_float(dt)), "euler_advect_smoke")
+
+    def step(self, num_iter, dt, n_steps=1, solver_order=RED_BLACK):
+        """the caller sequence of eulerian_fluid/src/fluid_ui.h:107-111"""
+        _check(self._lib.euler_step(self._h, int(num_iter), C.c_float(dt), int(solver_order), int(n_steps)), "euler_step")
+
+    def sampleField(self, xs, ys, field):
+        xs = np.ascontiguousarray(xs, np.float32).reshape(-1)
+        ys = np.ascontiguousarray(ys, np.float32).reshape(-1)
+        out = np.empty_like(xs)
+        _check(self._lib.euler_sample_field(self._h, int(field), xs.ctypes.data_as(C.POINTER(C.c_float)),
+                                            ys.ctypes.data_as(C.POINTER(C.c_float)),
+                                            out.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(xs.size)), "euler_sample_field")
+        return out
+
+    def residual(self):
+        mx, rms = C.c_float(), C.c_float()
+        _check(self._lib.euler_get_residual(self._h, C.byref(mx), C.byref(rms)), "euler_get_residual")
+        return float(mx.value), float(rms.value)
+
+    def synchronize(self):
+        _check(self._lib.euler_synchronize(self._h), "euler_synchronize")
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        _check(self._lib.euler_get_stream(self._h, C.byref(s)), "euler_get_stream")
+        return s.value or 0
+
+    @property
+    def launch_count(self):
+        n = C.c_longlong()
+        _check(self._lib.euler_get_launch_count(self._h, C.byref(n)), "euler_get_launch_count")
+        return n.value
+
+    def close(self):
+        if self._h:
+            self._lib.euler_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,75 @@
+// Shared plumbing of libflipgpu.so: error reporting, launch accounting, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include "../../include/flipgpu.h"
+
+namespace fg {
+
+void set_error(const char* fmt, ...);
+
+#define FG_CUDA(call)                                                                            \
+	do {                                                                                         \
+		cudaError_t e_ = (call);                                                                 \
+		if (e_ != cudaSuccess) {                                                                 \
+			fg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+			return FLIPGPU_ECUDA;                                                                \
+		}                                                                                        \
+	} while (0)
+
+#define FG_CHECK(cond, code, ...)       \
+	do {                                \
+		if (!(cond)) {                  \
+			fg::set_error(__VA_ARGS__); \
+			return code;                \
+		}                               \
+	} while (0)
+
+#define FG_TRY(expr)              \
+	do {                          \
+		int rc_ = (expr);         \
+		if (rc_ != FLIPGPU_OK) return rc_; \
+	} while (0)
+
+// cell types of flip_fluid.h:30-34
+enum : int { FLUID_CELL = 0, AIR_CELL = 1, SOLID_CELL = 2 };
+
+constexpr int kNumSMs = 148;  // B200
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Grid size for grid-stride kernels: whole waves of the 148 SMs, capped by the work available.
+inline unsigned wave_grid(size_t work_items, int threads, int ctas_per_sm = 8) {
+	size_t need = (work_items + threads - 1) / threads;
+	size_t full = (size_t)kNumSMs * ctas_per_sm;
+	if (need >= full) return (unsigned)full;
+	return (unsigned)(need ? need : 1);
+}
+
+struct LaunchCounter {
+	long long n = 0;
+};
+
+// Views used by the shared SOR projection (sor.cuh).  "fast" is the contiguous axis of the
+// storage: x for FlipFluid (fIX, flip_fluid.h:147-149), y for the Eulerian Fluid (ix, fluid.h:94-96).
+struct SorGrid {
+	int nf, ns;            // cells along the fast / slow axis
+	float* vel_f;          // velocity component along the fast axis, at the low-index face (u for FLIP, v for Euler)
+	float* vel_s;          // component along the slow axis (v for FLIP, u for Euler)
+	float* p;              // pressure accumulator
+	const float* s;        // 0 = solid, else open (flip_fluid.h:28)
+	const int* cell_type;  // only FLUID_CELL cells are updated (flip_fluid.h:462 / fluid.h:110)
+	const float* density;  // particle_density for the drift term, or nullptr
+	const float* rest;     // device scalar particle_rest_density, or nullptr
+	bool x_fast;           // true: fast axis is x (FLIP); false: fast axis is y (Euler).  Fixes the fp32
+	                       // association order of the divergence (flip_fluid.h:476 / fluid.h:122-123)
+};
+
+int sor_solve(const SorGrid& g, int iters, float cp, float omega, bool drift, int order, cudaStream_t st,
+              LaunchCounter* lc);
+int sor_residual(const SorGrid& g, bool drift, float* d_partials, int n_partials, float* h_out2, cudaStream_t st,
+                 LaunchCounter* lc);
+
+}  // namespace fg

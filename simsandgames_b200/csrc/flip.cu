@@ -1,0 +1,1189 @@
+// B200-native FLIP step behind the C ABI of include/flipgpu.h.
+// Replaces struct FlipFluid (reference flip_fluid/src/flip_fluid.h:13-582); every kernel cites the
+// reference lines whose arithmetic it reproduces.  Compiled with -fmad=false: fp32 products and sums
+// stay unfused and in the reference's association order, so per-particle phases are bit-exact against
+// the serial CPU step and only summation ORDER (P2G) or sweep ORDER (separation, red-black) differ.
+//
+// Data layout in HBM (DESIGN.md "layout"):
+//   grid   : u v prev_u prev_v p s density  float[C], cell_type int[C], x-fastest like fIX (flip_fluid.h:147)
+//   particles: pos/vel float2[P] x2 (ping-pong), physically sorted by spatial-hash cell (pIX order,
+//            descending caller id inside a cell -- exactly cell_particle_ids order, flip_fluid.h:196-197);
+//            orig[] = caller index of each slot == cell_particle_ids.
+//   hash   : num_cell_particles int[Hc], first_cell_particle int[Hc+1]  (bit-exact vs flip_fluid.h:169-198)
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+
+namespace fg {
+
+thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+constexpr int kThreads = 256;
+constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+struct Geo {  // constants every kernel needs, passed by value
+	int nx, ny, pnx, pny, np;
+	float h, inv_h, h2, r, p_inv;
+	float xmax_c, ymax_c;  // h*(nx-1), h*(ny-1): clamp bounds of the bilinear stencil (flip_fluid.h:301-302)
+};
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ int clampi(int a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
+__device__ __forceinline__ float clampf(float a, float lo, float hi) { return a < lo ? lo : (hi < a ? hi : a); }
+
+// spatial-hash cell, flip_fluid.h:174-176
+__device__ __forceinline__ int hash_cell(const Geo& g, float x, float y, int* cx = nullptr, int* cy = nullptr) {
+	int xi = clampi((int)(x * g.p_inv), 0, g.pnx - 1);
+	int yi = clampi((int)(y * g.p_inv), 0, g.pny - 1);
+	if (cx) { *cx = xi; *cy = yi; }
+	return xi + g.pnx * yi;
+}
+
+// bilinear stencil of flip_fluid.h:301-313 == :374-396 (Q2: same cell-centred offset for u, v and density)
+struct Stencil {
+	int x0, x1, y0, y1;
+	float w0, w1, w2, w3;  // d0..d3 of flip_fluid.h:388-391 for nodes (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+};
+__device__ __forceinline__ Stencil make_stencil(const Geo& g, float x, float y) {
+	x = clampf(x, g.h, g.xmax_c);
+	y = clampf(y, g.h, g.ymax_c);
+	Stencil st;
+	float xs = x - g.h2, ys = y - g.h2;
+	st.x0 = (int)(g.inv_h * xs);
+	float tx = g.inv_h * (xs - g.h * (float)st.x0);
+	st.x1 = min(1 + st.x0, g.nx - 2);
+	st.y0 = (int)(g.inv_h * ys);
+	float ty = g.inv_h * (ys - g.h * (float)st.y0);
+	st.y1 = min(1 + st.y0, g.ny - 2);
+	float sx = 1.f - tx, sy = 1.f - ty;
+	st.w0 = sx * sy; st.w1 = tx * sy; st.w2 = tx * ty; st.w3 = sx * ty;
+	return st;
+}
+
+__device__ __forceinline__ int warp_max(int v) {
+	for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// ------------------------------------------------------------------ F1 (+ first half of F2)
+// integrateParticles (flip_fluid.h:156-162) fused with the key + histogram of the counting sort (:169-177).
+template <bool INTEGRATE, bool BIN>
+__global__ void __launch_bounds__(kThreads) k_integrate_bin(Geo g, float2* __restrict__ pos, float2* __restrict__ vel,
+                                                            float dt, float gravity, int* __restrict__ keys,
+                                                            int* __restrict__ count) {
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < g.np; k += gridDim.x * blockDim.x) {
+		float2 p = pos[k];
+		if (INTEGRATE) {
+			float2 v = vel[k];
+			v.y += gravity * dt;
+			p.x += v.x * dt;
+			p.y += v.y * dt;
+			vel[k] = v;
+			pos[k] = p;
+		}
+		if (BIN) {
+			int key = hash_cell(g, p.x, p.y);
+			keys[k] = key;
+			atomicAdd(count + key, 1);  // integer histogram: the result is order-independent
+		}
+	}
+}
+
+// ------------------------------------------------------------------ F2: running sum (flip_fluid.h:180-186)
+// Three passes over the Hc counts: tile sums, scan of tile sums, tile rescan.  first[c] leaves this
+// stage INCLUSIVE (as :183); the fill's decrements turn it into the exclusive start (as :196).
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int* __restrict__ count, int n, int* __restrict__ tile_sum) {
+	size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+	int s = 0;
+	if (base + kScanItems <= (size_t)n) {
+		int4 a = *reinterpret_cast<const int4*>(count + base), b = *reinterpret_cast<const int4*>(count + base + 4);
+		s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+	} else {
+		for (int i = 0; i < kScanItems; i++) if (base + i < (size_t)n) s += count[base + i];
+	}
+	for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	__shared__ int ws[kScanThreads / 32];
+	if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int t = 0;
+		for (int i = 0; i < kScanThreads / 32; i++) t += ws[i];
+		tile_sum[blockIdx.x] = t;
+	}
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tile_offsets(int* __restrict__ tile_sum, int n_tiles) {
+	// single CTA: exclusive scan of the tile sums in place, 1024 at a time with a running carry
+	__shared__ int ws[32];
+	__shared__ int carry_s;
+	if (threadIdx.x == 0) carry_s = 0;
+	__syncthreads();
+	for (int base = 0; base < n_tiles; base += 1024) {
+		int i = base + threadIdx.x;
+		int v = i < n_tiles ? tile_sum[i] : 0;
+		int incl = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if ((threadIdx.x & 31) >= o) incl += t;
+		}
+		if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			int w = ws[threadIdx.x], wi = w;
+			for (int o = 1; o < 32; o <<= 1) {
+				int t = __shfl_up_sync(0xffffffffu, wi, o);
+				if (threadIdx.x >= o) wi += t;
+			}
+			ws[threadIdx.x] = wi - w;  // exclusive warp offsets
+		}
+		__syncthreads();
+		int carry = carry_s;
+		int excl = carry + ws[threadIdx.x >> 5] + incl - v;
+		if (i < n_tiles) tile_sum[i] = excl;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry_s = excl + v;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int* __restrict__ count, int n,
+                                                             const int* __restrict__ tile_off, int* __restrict__ first) {
+	size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+	int v[kScanItems];
+	if (base + kScanItems <= (size_t)n) {
+		int4 a = *reinterpret_cast<const int4*>(count + base), b = *reinterpret_cast<const int4*>(count + base + 4);
+		v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+	} else {
+		for (int i = 0; i < kScanItems; i++) v[i] = (base + i < (size_t)n) ? count[base + i] : 0;
+	}
+	for (int i = 1; i < kScanItems; i++) v[i] += v[i - 1];
+	int tot = v[kScanItems - 1], incl = tot;
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if ((threadIdx.x & 31) >= o) incl += t;
+	}
+	__shared__ int ws[kScanThreads / 32];
+	if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		int w = threadIdx.x < kScanThreads / 32 ? ws[threadIdx.x] : 0, wi = w;
+		for (int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, wi, o);
+			if (threadIdx.x >= o) wi += t;
+		}
+		if (threadIdx.x < kScanThreads / 32) ws[threadIdx.x] = wi - w;
+	}
+	__syncthreads();
+	int off = tile_off[blockIdx.x] + ws[threadIdx.x >> 5] + incl - tot;
+	if (base + kScanItems <= (size_t)n) {
+		int4 a = make_int4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
+		int4 b = make_int4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
+		*reinterpret_cast<int4*>(first + base) = a;
+		*reinterpret_cast<int4*>(first + base + 4) = b;
+		if (base + kScanItems == (size_t)n) first[n] = v[7] + off;  // guard entry, flip_fluid.h:186
+	} else {
+		for (int i = 0; i < kScanItems; i++)
+			if (base + i < (size_t)n) {
+				first[base + i] = v[i] + off;
+				if (base + i == (size_t)n - 1) first[n] = v[i] + off;
+			}
+	}
+}
+
+// ------------------------------------------------------------------ F2: fill (flip_fluid.h:189-198)
+// Slots are claimed with atomicSub (any order) ...
+__global__ void __launch_bounds__(kThreads) k_fill(int np, const int* __restrict__ keys, const int* __restrict__ orig,
+                                                   int* __restrict__ first, int* __restrict__ src, int* __restrict__ ids) {
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
+		int slot = atomicSub(first + keys[k], 1) - 1;
+		src[slot] = k;
+		ids[slot] = orig[k];
+	}
+}
+// ... and each cell's segment is then put into the reference's order: DESCENDING caller index (Q7),
+// which is what the serial decrement-on-fill of :196-197 produces.  Deterministic and bit-exact.
+__global__ void __launch_bounds__(kThreads) k_fixup_cells(int n_cells, const int* __restrict__ count,
+                                                          const int* __restrict__ first, int* __restrict__ src,
+                                                          int* __restrict__ ids) {
+	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+		int n = count[c];
+		if (n < 2) continue;
+		int b = first[c];
+		for (int i = 1; i < n; i++) {  // insertion sort, descending id; segments hold a handful of particles
+			int id = ids[b + i], sv = src[b + i];
+			int j = i - 1;
+			while (j >= 0 && ids[b + j] < id) {
+				ids[b + j + 1] = ids[b + j];
+				src[b + j + 1] = src[b + j];
+				j--;
+			}
+			ids[b + j + 1] = id;
+			src[b + j + 1] = sv;
+		}
+	}
+}
+
+// physical reorder into hash-cell order; also records each slot's bin (for the P2G search margin)
+template <bool COLORS>
+__global__ void __launch_bounds__(kThreads) k_reorder(Geo g, const int* __restrict__ src, const float2* __restrict__ pos_in,
+                                                      const float2* __restrict__ vel_in, const float* __restrict__ col_in,
+                                                      float2* __restrict__ pos_out, float2* __restrict__ vel_out,
+                                                      float* __restrict__ col_out, int* __restrict__ slot_key) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		int k = src[t];
+		float2 p = pos_in[k];
+		pos_out[t] = p;
+		vel_out[t] = vel_in[k];
+		slot_key[t] = hash_cell(g, p.x, p.y);
+		if (COLORS) {
+			col_out[3 * (size_t)t] = col_in[3 * (size_t)k];
+			col_out[3 * (size_t)t + 1] = col_in[3 * (size_t)k + 1];
+			col_out[3 * (size_t)t + 2] = col_in[3 * (size_t)k + 2];
+		}
+	}
+}
+
+// slots back to caller order (used by upload/readback of particle arrays)
+template <typename T, int W>
+__global__ void __launch_bounds__(kThreads) k_scatter_to_caller(int np, const int* __restrict__ orig,
+                                                                const T* __restrict__ in, T* __restrict__ out) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) {
+		size_t o = (size_t)orig[t];
+		for (int w = 0; w < W; w++) out[W * o + w] = in[W * (size_t)t + w];
+	}
+}
+__global__ void k_iota(int n, int* a) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = i;
+}
+__global__ void k_init_colors(int n, float* c) {  // flip_fluid.h:94-96
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		c[3 * (size_t)i] = 0.f; c[3 * (size_t)i + 1] = 0.f; c[3 * (size_t)i + 2] = 1.f;
+	}
+}
+
+// ------------------------------------------------------------------ F3: separation sweep (flip_fluid.h:201-250)
+// The reference sweep is a serial Gauss-Seidel over particles in caller order with an asymmetric pair
+// update (Q1); no parallel schedule reproduces it.  This is the deterministic parallel schedule: one
+// Jacobi sweep per launch -- every particle gathers, from the positions at the start of the sweep, the
+// symmetric half-overlap push of :231-235 from each neighbour in its 3x3 hash window (window from the
+// CURRENT position as :208-213, bins from before the first sweep as Q6).  Neighbours are visited
+// row by row in slot order; oracle/flip_oracle.c:orcflip_separate_jacobi is the same schedule on the CPU
+// and this kernel is bit-exact against it.  Statistical distance to the serial sweep: tests T3.
+template <bool COLORS>
+__global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
+                                                       float2* __restrict__ pos_out, const float* __restrict__ col_in,
+                                                       float* __restrict__ col_out) {
+	const float min_dist = 2.f * g.r;
+	const float min_dist_sq = min_dist * min_dist;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		float2 p = pos_in[t];
+		float ax = p.x, ay = p.y;
+		float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+		if (COLORS) { c0 = col_in[3 * (size_t)t]; c1 = col_in[3 * (size_t)t + 1]; c2 = col_in[3 * (size_t)t + 2]; }
+		int pxi = (int)(p.x * g.p_inv), pyi = (int)(p.y * g.p_inv);
+		int x0 = max(pxi - 1, 0), y0 = max(pyi - 1, 0);
+		int x1 = min(pxi + 1, g.pnx - 1), y1 = min(pyi + 1, g.pny - 1);
+		if (x0 <= x1)
+			for (int yi = y0; yi <= y1; yi++) {
+				int a = first[x0 + g.pnx * yi], b = first[x1 + g.pnx * yi + 1];
+				for (int j = a; j < b; j++) {
+					if (j == t) continue;
+					float2 q = pos_in[j];
+					float dx = q.x - p.x, dy = q.y - p.y;
+					float d2 = dx * dx + dy * dy;
+					if (d2 > min_dist_sq || d2 == 0.f) continue;
+					float d = sqrtf(d2);
+					float sc = .5f * (min_dist - d) / d;
+					ax -= dx * sc;
+					ay -= dy * sc;
+					if (COLORS) {  // colour diffusion toward the pair mean, flip_fluid.h:239-245
+						float q0 = col_in[3 * (size_t)j], q1 = col_in[3 * (size_t)j + 1], q2 = col_in[3 * (size_t)j + 2];
+						c0 += .001f * ((c0 + q0) / 2.f - c0);
+						c1 += .001f * ((c1 + q1) / 2.f - c1);
+						c2 += .001f * ((c2 + q2) / 2.f - c2);
+					}
+				}
+			}
+		pos_out[t] = make_float2(ax, ay);
+		if (COLORS) { col_out[3 * (size_t)t] = c0; col_out[3 * (size_t)t + 1] = c1; col_out[3 * (size_t)t + 2] = c2; }
+	}
+}
+
+// ------------------------------------------------------------------ F5 prep: cell_type from s (flip_fluid.h:348-350)
+__global__ void __launch_bounds__(kThreads) k_cell_type_from_s(int n, const float* __restrict__ s, int* __restrict__ cell_type) {
+	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+		cell_type[c] = s[c] == 0.f ? SOLID_CELL : AIR_CELL;
+}
+
+// ------------------------------------------------------------------ F4 + F5 marking
+// handleParticleCollisions (flip_fluid.h:254-289) fused with the fluid-cell marking of :352-359 and
+// with the bookkeeping the gather-form P2G needs: how far (in hash cells) a particle now sits from the
+// bin it was sorted into.
+template <bool COLLIDE>
+__global__ void __launch_bounds__(kThreads) k_collide_mark(Geo g, float2* __restrict__ pos, float2* __restrict__ vel, float ox,
+                                                           float oy, float ovx, float ovy, float orad,
+                                                           int* __restrict__ cell_type, const int* __restrict__ slot_key,
+                                                           int* __restrict__ margin) {
+	const float md = g.r + orad, md2 = md * md;
+	const float min_x = g.h + g.r, max_x = g.h * (float)(g.nx - 1) - g.r;
+	const float min_y = g.h + g.r, max_y = g.h * (float)(g.ny - 1) - g.r;
+	int m = 0;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		float2 p = pos[t];
+		if (COLLIDE) {
+			float2 v = vel[t];
+			float dx = p.x - ox, dy = p.y - oy;
+			if (dx * dx + dy * dy < md2) { v.x = ovx; v.y = ovy; }  // Q12: velocity only, no push-out
+			if (p.x < min_x) { p.x = min_x; v.x = 0.f; }
+			if (p.x > max_x) { p.x = max_x; v.x = 0.f; }
+			if (p.y < min_y) { p.y = min_y; v.y = 0.f; }
+			if (p.y > max_y) { p.y = max_y; v.y = 0.f; }
+			pos[t] = p;
+			vel[t] = v;
+		}
+		if (cell_type) {
+			int xi = clampi((int)(g.inv_h * p.x), 0, g.nx - 1);
+			int yi = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
+			int c = xi + g.nx * yi;
+			if (cell_type[c] == AIR_CELL) cell_type[c] = FLUID_CELL;  // all racing writers store the same value
+		}
+		if (slot_key) {
+			int cx, cy;
+			hash_cell(g, p.x, p.y, &cx, &cy);
+			int key = slot_key[t];
+			int kx = key % g.pnx, ky = key / g.pnx;
+			m = max(m, max(abs(cx - kx), abs(cy - ky)));
+		}
+	}
+	if (slot_key) {
+		m = warp_max(m);
+		if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(margin, m);
+	}
+}
+
+// ------------------------------------------------------------------ F6 + F7: sort-ordered, atomic-free P2G
+// transferVelocities(true) splat + normalise + solid restore (flip_fluid.h:362-403,432-446) and
+// updateParticleDensity (:292-319) in GATHER form: one thread per grid node walks the hash rows that
+// can hold a contributing particle (contiguous slot ranges, because particles are sorted in pIX order)
+// and accumulates its own node in slot order -- no atomics, run-to-run bit-stable.  The per-particle
+// arithmetic is the reference's; only the order of the adds into a node differs (slot order instead of
+// caller order).  du, dv and particle_density are one array here: the reference computes the same
+// weights three times (bit-equal except aliased border cells).
+__global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict__ first, const float2* __restrict__ pos,
+                                                    const float2* __restrict__ vel, const int* __restrict__ margin_p,
+                                                    const int* __restrict__ cell_type, float* __restrict__ u,
+                                                    float* __restrict__ v, float* __restrict__ prev_u,
+                                                    float* __restrict__ prev_v, float* __restrict__ dens,
+                                                    float* __restrict__ p) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int j = blockIdx.y * blockDim.y + threadIdx.y;
+	if (i >= g.nx || j >= g.ny) return;
+	const int margin = *margin_p;
+	// positions whose base cell x0 is i-1 or i lie in [h(i-1)+h2, h(i+1)+h2); pad for fp32 rounding
+	float pad = 1e-5f * fmaxf(g.xmax_c, g.ymax_c);
+	float xlo = g.h * (float)(i - 1) + g.h2 - pad, xhi = g.h * (float)(i + 1) + g.h2 + pad;
+	float ylo = g.h * (float)(j - 1) + g.h2 - pad, yhi = g.h * (float)(j + 1) + g.h2 + pad;
+	int cx0 = clampi((int)(xlo * g.p_inv) - margin, 0, g.pnx - 1), cx1 = clampi((int)(xhi * g.p_inv) + margin, 0, g.pnx - 1);
+	int cy0 = clampi((int)(ylo * g.p_inv) - margin, 0, g.pny - 1), cy1 = clampi((int)(yhi * g.p_inv) + margin, 0, g.pny - 1);
+	// positions outside the grid are clamped onto the border nodes by the stencil (:301-302), wherever they were binned
+	if (i <= 1) cx0 = 0;
+	if (i >= g.nx - 2) cx1 = g.pnx - 1;
+	if (j <= 1) cy0 = 0;
+	if (j >= g.ny - 2) cy1 = g.pny - 1;
+	float su = 0.f, sv = 0.f, sw = 0.f;
+	for (int cy = cy0; cy <= cy1; cy++) {
+		int a = first[cx0 + g.pnx * cy], b = first[cx1 + g.pnx * cy + 1];
+		for (int t = a; t < b; t++) {
+			float2 pp = pos[t];
+			Stencil st = make_stencil(g, pp.x, pp.y);
+			bool mx0 = st.x0 == i, mx1 = st.x1 == i, my0 = st.y0 == j, my1 = st.y1 == j;
+			if (!((mx0 | mx1) & (my0 | my1))) continue;
+			float2 pv = vel[t];
+			if (mx0 & my0) { su += pv.x * st.w0; sv += pv.y * st.w0; sw += st.w0; }
+			if (mx1 & my0) { su += pv.x * st.w1; sv += pv.y * st.w1; sw += st.w1; }
+			if (mx1 & my1) { su += pv.x * st.w2; sv += pv.y * st.w2; sw += st.w2; }
+			if (mx0 & my1) { su += pv.x * st.w3; sv += pv.y * st.w3; sw += st.w3; }
+		}
+	}
+	int c = i + g.nx * j;
+	if (sw > 0.f) { su /= sw; sv /= sw; }  // :433-435
+	// restore solid cells, :437-445 (prev_u/prev_v of :340-341 == the values still in u/v here)
+	int ct = cell_type[c];
+	bool solid = ct == SOLID_CELL;
+	if (solid || (i > 0 && cell_type[c - 1] == SOLID_CELL)) su = u[c];
+	if (solid || (j > 0 && cell_type[c - g.nx] == SOLID_CELL)) sv = v[c];
+	u[c] = su; v[c] = sv;
+	prev_u[c] = su; prev_v[c] = sv;  // the copy solveIncompressibility makes at :453-454
+	dens[c] = sw;
+	p[c] = 0.f;                     // :452
+}
+
+// ------------------------------------------------------------------ F7 latch (flip_fluid.h:321-332, Q14)
+__global__ void __launch_bounds__(256) k_rest_partials(int n, const int* __restrict__ cell_type, const float* __restrict__ dens,
+                                                       const float* __restrict__ rest, float* __restrict__ partials) {
+	if (*rest != 0.f) return;
+	float s = 0.f, cnt = 0.f;
+	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+		if (cell_type[c] == FLUID_CELL) { s += dens[c]; cnt += 1.f; }
+	for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+	__shared__ float ws[2][8];
+	if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = s; ws[1][threadIdx.x >> 5] = cnt; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int i = 1; i < 8; i++) { s += ws[0][i]; cnt += ws[1][i]; }
+		partials[2 * blockIdx.x] = s; partials[2 * blockIdx.x + 1] = cnt;
+	}
+}
+__global__ void k_rest_latch(int n_partials, const float* __restrict__ partials, float* __restrict__ rest) {
+	if (threadIdx.x != 0 || *rest != 0.f) return;
+	double s = 0.0, cnt = 0.0;
+	for (int i = 0; i < n_partials; i++) { s += partials[2 * i]; cnt += partials[2 * i + 1]; }
+	if (cnt > 0.0) *rest = (float)(s / cnt);
+}
+
+// ------------------------------------------------------------------ F8: G2P (flip_fluid.h:404-429)
+__global__ void __launch_bounds__(kThreads) k_g2p(Geo g, const float2* __restrict__ pos, float2* __restrict__ vel,
+                                                  const float* __restrict__ u, const float* __restrict__ v,
+                                                  const float* __restrict__ prev_u, const float* __restrict__ prev_v,
+                                                  const int* __restrict__ cell_type, float flip_ratio) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		float2 p = pos[t];
+		float2 pv = vel[t];
+		Stencil st = make_stencil(g, p.x, p.y);
+		int n0 = st.x0 + g.nx * st.y0, n1 = st.x1 + g.nx * st.y0, n2 = st.x1 + g.nx * st.y1, n3 = st.x0 + g.nx * st.y1;
+		int ct0 = cell_type[n0], ct1 = cell_type[n1], ct2 = cell_type[n2], ct3 = cell_type[n3];
+#pragma unroll
+		for (int comp = 0; comp < 2; comp++) {
+			const float* f = comp == 0 ? u : v;
+			const float* pf = comp == 0 ? prev_u : prev_v;
+			int off = comp == 0 ? 1 : g.nx;
+			// Q3: the reference reads cell_type[n-off] below index 0 when y0==0; policy: out of range => not fluid
+			float k0 = (ct0 == FLUID_CELL || (n0 - off >= 0 && cell_type[n0 - off] == FLUID_CELL)) ? 1.f : 0.f;
+			float k1 = (ct1 == FLUID_CELL || (n1 - off >= 0 && cell_type[n1 - off] == FLUID_CELL)) ? 1.f : 0.f;
+			float k2 = (ct2 == FLUID_CELL || (n2 - off >= 0 && cell_type[n2 - off] == FLUID_CELL)) ? 1.f : 0.f;
+			float k3 = (ct3 == FLUID_CELL || (n3 - off >= 0 && cell_type[n3 - off] == FLUID_CELL)) ? 1.f : 0.f;
+			float dsum = k0 * st.w0 + k1 * st.w1 + k2 * st.w2 + k3 * st.w3;
+			if (dsum > 0.f) {
+				float f0 = f[n0], f1 = f[n1], f2 = f[n2], f3 = f[n3];
+				float pic = (k0 * st.w0 * f0 + k1 * st.w1 * f1 + k2 * st.w2 * f2 + k3 * st.w3 * f3) / dsum;
+				float corr = (k0 * st.w0 * (f0 - pf[n0]) + k1 * st.w1 * (f1 - pf[n1]) + k2 * st.w2 * (f2 - pf[n2]) +
+				              k3 * st.w3 * (f3 - pf[n3])) / dsum;
+				float cur = comp == 0 ? pv.x : pv.y;
+				float flipv = cur + corr;
+				float nv = (1.f - flip_ratio) * pic + flip_ratio * flipv;
+				if (comp == 0) pv.x = nv; else pv.y = nv;
+			}
+		}
+		vel[t] = pv;
+	}
+}
+
+// ------------------------------------------------------------------ F10: render state (flip_fluid.h:498-557)
+__global__ void __launch_bounds__(kThreads) k_particle_colors(Geo g, const float2* __restrict__ pos, float* __restrict__ col,
+                                                              const float* __restrict__ dens, const float* __restrict__ rest_p) {
+	float rest = *rest_p;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		float r = clampf(col[3 * (size_t)t] - .01f, 0.f, 1.f);
+		float gg = clampf(col[3 * (size_t)t + 1] - .01f, 0.f, 1.f);
+		float b = clampf(col[3 * (size_t)t + 2] + .01f, 0.f, 1.f);
+		if (rest > 0.f) {
+			float2 p = pos[t];
+			int xi = clampi((int)(g.inv_h * p.x), 1, g.nx - 1);
+			int yi = clampi((int)(g.inv_h * p.y), 1, g.ny - 1);
+			float rel = dens[xi + g.nx * yi] / rest;
+			if (rel < .7f) { r = .8f; gg = .8f; b = 1.f; }
+		}
+		col[3 * (size_t)t] = r; col[3 * (size_t)t + 1] = gg; col[3 * (size_t)t + 2] = b;
+	}
+}
+__global__ void __launch_bounds__(kThreads) k_cell_colors(int n, const int* __restrict__ cell_type, const float* __restrict__ dens,
+                                                          const float* __restrict__ rest_p, float* __restrict__ cc) {
+	float rest = *rest_p;
+	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+		float r = 0.f, gg = 0.f, b = 0.f;
+		int ct = cell_type[c];
+		if (ct == SOLID_CELL) { r = gg = b = .5f; }
+		else if (ct == FLUID_CELL) {  // setSciColor(i, d, 0, 2), :521-540
+			float val = dens[c];
+			if (rest > 0.f) val /= rest;
+			val = clampf(val, 0.f, 2.f - .0001f);
+			float span = 2.f - 0.f;
+			val = span == 0.f ? .5f : (val - 0.f) / span;
+			float m = .25f;
+			int num = (int)(val / m);
+			float sc = (val - (float)num * m) / m;
+			switch (num) {
+				case 0: r = 0.f; gg = sc; b = 1.f; break;
+				case 1: r = 0.f; gg = 1.f; b = 1.f - sc; break;
+				case 2: r = sc; gg = 1.f; b = 0.f; break;
+				case 3: r = 1.f; gg = 1.f - sc; b = 0.f; break;
+			}
+		}
+		cc[3 * (size_t)c] = r; cc[3 * (size_t)c + 1] = gg; cc[3 * (size_t)c + 2] = b;
+	}
+}
+
+// ------------------------------------------------------------------ setObstacle (flip_fluid/src/main.cpp:104-122, Q10)
+__global__ void __launch_bounds__(256) k_set_obstacle(Geo g, float x, float y, float vx, float vy, float rad,
+                                                      float* __restrict__ s, float* __restrict__ u, float* __restrict__ v) {
+	int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+	int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+	if (i >= g.nx - 2 || j >= g.ny - 2) return;
+	int c = i + g.nx * j;
+	float dx = g.h * (.5f + (float)i) - x, dy = g.h * (.5f + (float)j) - y;
+	float sv = 1.f;
+	if (dx * dx + dy * dy < rad * rad) {
+		sv = 0.f;
+		u[c] = vx; u[c + 1] = vx; v[c] = vy; v[c + g.nx] = vy;  // duplicates across cells store the same value
+	}
+	s[c] = sv;
+}
+
+}  // namespace fg
+
+// =================================================================== host side
+using namespace fg;
+
+struct FlipSim {
+	FlipDims d{};
+	int device = 0;
+	cudaStream_t st = nullptr;
+	float *u = nullptr, *v = nullptr, *prev_u = nullptr, *prev_v = nullptr, *p = nullptr, *s = nullptr, *dens = nullptr;
+	int* cell_type = nullptr;
+	float* cell_color = nullptr;  // lazily allocated
+	float2* pos[2] = {nullptr, nullptr};
+	float2* vel[2] = {nullptr, nullptr};
+	float* col[2] = {nullptr, nullptr};  // lazily allocated
+	int* orig[2] = {nullptr, nullptr};   // caller index per slot; orig[cur] doubles as cell_particle_ids
+	int cur = 0;
+	int *keys = nullptr, *src = nullptr, *slot_key = nullptr, *count = nullptr, *first = nullptr, *tile_sum = nullptr;
+	float* d_rest = nullptr;   // device scalar particle_rest_density
+	int* d_margin = nullptr;   // device scalar, P2G search margin in hash cells
+	float* d_partials = nullptr;
+	float* h_pinned = nullptr;  // [0] rest mirror
+	bool identity = true;       // slot order == caller order
+	bool bins_valid = false;
+	bool rest_seen = false;
+	bool timings_on = false;
+	float ph_ms[FLIP_PH_COUNT] = {0};
+	cudaEvent_t ev[FLIP_PH_COUNT + 1] = {nullptr};
+	bool ev_pending = false;
+	LaunchCounter lc;
+};
+
+namespace {
+constexpr int kPartials = 1024;
+
+Geo geo(const FlipSim* f) {
+	Geo g;
+	g.nx = f->d.f_num_x; g.ny = f->d.f_num_y; g.pnx = f->d.p_num_x; g.pny = f->d.p_num_y; g.np = f->d.num_particles;
+	g.h = f->d.h; g.inv_h = f->d.f_inv_spacing; g.h2 = .5f * f->d.h; g.r = f->d.particle_radius; g.p_inv = f->d.p_inv_spacing;
+	g.xmax_c = f->d.h * (float)(f->d.f_num_x - 1);
+	g.ymax_c = f->d.h * (float)(f->d.f_num_y - 1);
+	return g;
+}
+unsigned pgrid(const FlipSim* f) { return wave_grid((size_t)std::max(f->d.num_particles, 1), kThreads); }
+
+int ensure_colors(FlipSim* f) {
+	if (f->col[0]) return FLIPGPU_OK;
+	size_t n = 3 * (size_t)std::max(f->d.max_particles, 1);
+	FG_CUDA(cudaMalloc(&f->col[0], n * 4));
+	FG_CUDA(cudaMalloc(&f->col[1], n * 4));
+	k_init_colors<<<wave_grid(f->d.max_particles, kThreads), kThreads, 0, f->st>>>(f->d.max_particles, f->col[0]);
+	k_init_colors<<<wave_grid(f->d.max_particles, kThreads), kThreads, 0, f->st>>>(f->d.max_particles, f->col[1]);
+	f->lc.n += 2;
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+int ensure_cell_colors(FlipSim* f) {
+	if (f->cell_color) return FLIPGPU_OK;
+	FG_CUDA(cudaMalloc(&f->cell_color, 3 * (size_t)f->d.f_num_cells * 4));
+	FG_CUDA(cudaMemsetAsync(f->cell_color, 0, 3 * (size_t)f->d.f_num_cells * 4, f->st));
+	return FLIPGPU_OK;
+}
+
+// put every particle array back into caller order (slot k == caller particle k)
+int unsort(FlipSim* f) {
+	if (f->identity) return FLIPGPU_OK;
+	int np = f->d.num_particles, c = f->cur, n = 1 - c;
+	if (np > 0) {
+		unsigned gr = pgrid(f);
+		k_scatter_to_caller<float2, 1><<<gr, kThreads, 0, f->st>>>(np, f->orig[c], f->pos[c], f->pos[n]);
+		k_scatter_to_caller<float2, 1><<<gr, kThreads, 0, f->st>>>(np, f->orig[c], f->vel[c], f->vel[n]);
+		f->lc.n += 2;
+		if (f->col[0]) {
+			k_scatter_to_caller<float, 3><<<gr, kThreads, 0, f->st>>>(np, f->orig[c], f->col[c], f->col[n]);
+			f->lc.n++;
+		}
+		k_iota<<<gr, kThreads, 0, f->st>>>(np, f->orig[n]);
+		f->lc.n++;
+		FG_CUDA(cudaGetLastError());
+	}
+	f->cur = n;
+	f->identity = true;
+	f->bins_valid = false;
+	return FLIPGPU_OK;
+}
+
+void phase_mark(FlipSim* f, int idx) {
+	if (f->timings_on) cudaEventRecord(f->ev[idx], f->st);
+}
+void collect_timings(FlipSim* f) {
+	if (!f->ev_pending) return;
+	cudaEventSynchronize(f->ev[FLIP_PH_COUNT]);
+	for (int i = 0; i < FLIP_PH_COUNT; i++) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, f->ev[i], f->ev[i + 1]) == cudaSuccess) f->ph_ms[i] += ms;
+	}
+	f->ev_pending = false;
+}
+
+// F2: counting sort into hash-cell order.  keys/count must already hold this step's histogram.
+int bin_from_histogram(FlipSim* f) {
+	Geo g = geo(f);
+	int Hc = f->d.p_num_cells, np = g.np;
+	int tiles = (int)cdiv((size_t)Hc, kScanTile);
+	k_scan_tile_sums<<<tiles, kScanThreads, 0, f->st>>>(f->count, Hc, f->tile_sum);
+	k_scan_tile_offsets<<<1, 1024, 0, f->st>>>(f->tile_sum, tiles);
+	k_scan_tiles<<<tiles, kScanThreads, 0, f->st>>>(f->count, Hc, f->tile_sum, f->first);
+	f->lc.n += 3;
+	int c = f->cur, n = 1 - c;
+	if (np > 0) {
+		k_fill<<<pgrid(f), kThreads, 0, f->st>>>(np, f->keys, f->orig[c], f->first, f->src, f->orig[n]);
+		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count, f->first, f->src, f->orig[n]);
+		if (f->col[0])
+			k_reorder<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], f->slot_key);
+		else
+			k_reorder<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr, f->slot_key);
+		f->lc.n += 3;
+		f->cur = n;
+		f->identity = false;
+	}
+	FG_CUDA(cudaGetLastError());
+	f->bins_valid = true;
+	return FLIPGPU_OK;
+}
+
+int integrate_and_bin(FlipSim* f, bool integrate, bool bin, float dt, float gravity) {
+	Geo g = geo(f);
+	int c = f->cur;
+	if (bin) FG_CUDA(cudaMemsetAsync(f->count, 0, (size_t)f->d.p_num_cells * 4, f->st));
+	if (g.np > 0) {
+		if (integrate && bin) k_integrate_bin<true, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], dt, gravity, f->keys, f->count);
+		else if (integrate) k_integrate_bin<true, false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], dt, gravity, f->keys, f->count);
+		else if (bin) k_integrate_bin<false, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], dt, gravity, f->keys, f->count);
+		f->lc.n++;
+		FG_CUDA(cudaGetLastError());
+	}
+	if (bin) FG_TRY(bin_from_histogram(f));
+	return FLIPGPU_OK;
+}
+
+int separate(FlipSim* f, int iters, bool colors) {
+	Geo g = geo(f);
+	if (g.np == 0) return FLIPGPU_OK;
+	if (colors) FG_TRY(ensure_colors(f));
+	// Sweeps ping-pong between the two position buffers; velocities (and ids) stay in buffer `cur`,
+	// so after an odd number of sweeps the result is copied back rather than swapping every array.
+	int c = f->cur;
+	float2* a = f->pos[c];
+	float2* b = f->pos[1 - c];
+	float* ca = colors ? f->col[c] : nullptr;
+	float* cb = colors ? f->col[1 - c] : nullptr;
+	for (int it = 0; it < iters; it++) {
+		if (colors) k_separate<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb);
+		else k_separate<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr);
+		f->lc.n++;
+		std::swap(a, b);
+		std::swap(ca, cb);
+	}
+	FG_CUDA(cudaGetLastError());
+	if (a != f->pos[c]) {
+		FG_CUDA(cudaMemcpyAsync(f->pos[c], a, (size_t)g.np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st));
+		if (colors) FG_CUDA(cudaMemcpyAsync(f->col[c], ca, 3 * (size_t)g.np * 4, cudaMemcpyDeviceToDevice, f->st));
+	}
+	return FLIPGPU_OK;
+}
+
+int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad) {
+	Geo g = geo(f);
+	int c = f->cur;
+	if (mark) {
+		k_cell_type_from_s<<<wave_grid(f->d.f_num_cells, kThreads), kThreads, 0, f->st>>>(f->d.f_num_cells, f->s, f->cell_type);
+		f->lc.n++;
+		FG_CUDA(cudaMemsetAsync(f->d_margin, 0, sizeof(int), f->st));
+	}
+	if (g.np > 0) {
+		int* ct = mark ? f->cell_type : nullptr;
+		const int* sk = mark ? f->slot_key : nullptr;
+		if (collide) k_collide_mark<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, sk, f->d_margin);
+		else k_collide_mark<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, sk, f->d_margin);
+		f->lc.n++;
+	}
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+int p2g(FlipSim* f) {
+	Geo g = geo(f);
+	int c = f->cur;
+	dim3 block(32, 8);
+	dim3 grid(cdiv(g.nx, block.x), cdiv(g.ny, block.y));
+	k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->first, f->pos[c], f->vel[c], f->d_margin, f->cell_type, f->u, f->v,
+	                                        f->prev_u, f->prev_v, f->dens, f->p);
+	f->lc.n++;
+	if (!f->rest_seen) {
+		k_rest_partials<<<kPartials, 256, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest, f->d_partials);
+		k_rest_latch<<<1, 32, 0, f->st>>>(kPartials, f->d_partials, f->d_rest);
+		f->lc.n += 2;
+		// mirror the scalar into pinned memory; once a later call sees it non-zero the latch kernels stop
+		FG_CUDA(cudaMemcpyAsync(f->h_pinned, f->d_rest, sizeof(float), cudaMemcpyDeviceToHost, f->st));
+	}
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+SorGrid sor_view(FlipSim* f) {
+	SorGrid g;
+	g.nf = f->d.f_num_x; g.ns = f->d.f_num_y;
+	g.vel_f = f->u; g.vel_s = f->v; g.p = f->p; g.s = f->s; g.cell_type = f->cell_type;
+	g.density = f->dens; g.rest = f->d_rest; g.x_fast = true;
+	return g;
+}
+
+int g2p(FlipSim* f, float flip_ratio) {
+	Geo g = geo(f);
+	if (g.np == 0) return FLIPGPU_OK;
+	int c = f->cur;
+	k_g2p<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio);
+	f->lc.n++;
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+int colors(FlipSim* f) {
+	Geo g = geo(f);
+	FG_TRY(ensure_colors(f));
+	FG_TRY(ensure_cell_colors(f));
+	if (g.np > 0) {
+		k_particle_colors<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[f->cur], f->col[f->cur], f->dens, f->d_rest);
+		f->lc.n++;
+	}
+	k_cell_colors<<<wave_grid(f->d.f_num_cells, kThreads), kThreads, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest, f->cell_color);
+	f->lc.n++;
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t field_count(const FlipSim* f, int field) {
+	size_t C = f->d.f_num_cells, P = f->d.num_particles, H = f->d.p_num_cells;
+	switch (field) {
+		case FLIP_CELL_COLOR: return 3 * C;
+		case FLIP_PARTICLE_POS: case FLIP_PARTICLE_VEL: return 2 * P;
+		case FLIP_PARTICLE_COLOR: return 3 * P;
+		case FLIP_NUM_CELL_PARTICLES: return H;
+		case FLIP_FIRST_CELL_PARTICLE: return H + 1;
+		case FLIP_CELL_PARTICLE_IDS: return P;
+		default: return C;
+	}
+}
+void* grid_field_ptr(FlipSim* f, int field) {
+	switch (field) {
+		case FLIP_U: return f->u; case FLIP_V: return f->v;
+		case FLIP_DU: case FLIP_DV: case FLIP_PARTICLE_DENSITY: return f->dens;  // one array, see k_p2g_gather
+		case FLIP_PREV_U: return f->prev_u; case FLIP_PREV_V: return f->prev_v;
+		case FLIP_P: return f->p; case FLIP_S: return f->s; case FLIP_CELL_TYPE: return f->cell_type;
+		default: return nullptr;
+	}
+}
+}  // namespace
+
+extern "C" {
+
+const char* flipgpu_last_error(void) { return fg::g_err; }
+int flipgpu_version(void) { return 100; }
+int flipgpu_device_count(int* count) {
+	FG_CHECK(count, FLIPGPU_EINVAL, "count is null");
+	cudaError_t e = cudaGetDeviceCount(count);
+	if (e != cudaSuccess) { *count = 0; fg::set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return FLIPGPU_ENODEV; }
+	return FLIPGPU_OK;
+}
+
+int flip_create(const FlipParams* pr, FlipSim** out) {
+	FG_CHECK(pr && out, FLIPGPU_EINVAL, "flip_create: null argument");
+	FG_CHECK(pr->spacing > 0 && pr->particle_radius > 0 && pr->width > 0 && pr->height > 0 && pr->max_particles >= 0,
+	         FLIPGPU_EINVAL, "flip_create: non-positive geometry");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		fg::set_error("flip_create: no CUDA device (this library has no CPU fallback)");
+		return FLIPGPU_ENODEV;
+	}
+	int dev = pr->device;
+	if (dev < 0) FG_CUDA(cudaGetDevice(&dev));
+	FG_CHECK(dev < ndev, FLIPGPU_EINVAL, "flip_create: device %d of %d", dev, ndev);
+	FlipSim* f = new FlipSim;
+	f->device = dev;
+	DeviceGuard guard(dev);
+	// derived sizes in fp32, verbatim order of flip_fluid.h:69-74,103-106
+	FlipDims& d = f->d;
+	d.density = pr->density;
+	d.f_num_x = (int)(1 + pr->width / pr->spacing);
+	d.f_num_y = (int)(1 + pr->height / pr->spacing);
+	d.f_num_cells = d.f_num_x * d.f_num_y;
+	d.h = std::max(pr->width / d.f_num_x, pr->height / d.f_num_y);
+	d.f_inv_spacing = 1 / d.h;
+	d.max_particles = pr->max_particles;
+	d.particle_radius = pr->particle_radius;
+	d.p_inv_spacing = 1 / (2.2f * pr->particle_radius);
+	d.p_num_x = (int)(1 + pr->width * d.p_inv_spacing);
+	d.p_num_y = (int)(1 + pr->height * d.p_inv_spacing);
+	long long hc = (long long)d.p_num_x * d.p_num_y;
+	if (hc >= (1ll << 31) - 8 || (long long)d.f_num_x * d.f_num_y >= (1ll << 31)) {
+		delete f;
+		fg::set_error("flip_create: grid too large for int32 indices (shard it)");
+		return FLIPGPU_EINVAL;
+	}
+	d.p_num_cells = d.p_num_x * d.p_num_y;
+	d.num_particles = 0;
+	FG_CUDA(cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking));
+	size_t C = d.f_num_cells, M = std::max(d.max_particles, 1), H = d.p_num_cells;
+	float** grids[] = {&f->u, &f->v, &f->prev_u, &f->prev_v, &f->p, &f->s, &f->dens};
+	for (float** gp : grids) {
+		FG_CUDA(cudaMalloc(gp, C * 4));
+		FG_CUDA(cudaMemsetAsync(*gp, 0, C * 4, f->st));
+	}
+	FG_CUDA(cudaMalloc(&f->cell_type, C * 4));
+	FG_CUDA(cudaMemsetAsync(f->cell_type, 0, C * 4, f->st));
+	for (int b = 0; b < 2; b++) {
+		FG_CUDA(cudaMalloc(&f->pos[b], M * sizeof(float2)));
+		FG_CUDA(cudaMalloc(&f->vel[b], M * sizeof(float2)));
+		FG_CUDA(cudaMalloc(&f->orig[b], M * 4));
+		FG_CUDA(cudaMemsetAsync(f->pos[b], 0, M * sizeof(float2), f->st));
+		FG_CUDA(cudaMemsetAsync(f->vel[b], 0, M * sizeof(float2), f->st));
+		k_iota<<<wave_grid(M, kThreads), kThreads, 0, f->st>>>((int)M, f->orig[b]);
+	}
+	FG_CUDA(cudaMalloc(&f->keys, M * 4));
+	FG_CUDA(cudaMalloc(&f->src, M * 4));
+	FG_CUDA(cudaMalloc(&f->slot_key, M * 4));
+	FG_CUDA(cudaMalloc(&f->count, H * 4));
+	FG_CUDA(cudaMalloc(&f->first, (H + 1) * 4));
+	FG_CUDA(cudaMemsetAsync(f->count, 0, H * 4, f->st));
+	FG_CUDA(cudaMemsetAsync(f->first, 0, (H + 1) * 4, f->st));
+	FG_CUDA(cudaMemsetAsync(f->src, 0, M * 4, f->st));
+	FG_CUDA(cudaMalloc(&f->tile_sum, (size_t)(cdiv(H, kScanTile) + 1) * 4));
+	FG_CUDA(cudaMalloc(&f->d_rest, 4));
+	FG_CUDA(cudaMalloc(&f->d_margin, 4));
+	FG_CUDA(cudaMemsetAsync(f->d_rest, 0, 4, f->st));
+	FG_CUDA(cudaMemsetAsync(f->d_margin, 0, 4, f->st));
+	FG_CUDA(cudaMalloc(&f->d_partials, (3 * kPartials + 8) * 4));
+	FG_CUDA(cudaMallocHost(&f->h_pinned, 64));
+	f->h_pinned[0] = 0.f;
+	for (int i = 0; i <= FLIP_PH_COUNT; i++) FG_CUDA(cudaEventCreate(&f->ev[i]));
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	*out = f;
+	return FLIPGPU_OK;
+}
+
+int flip_destroy(FlipSim* f) {
+	if (!f) return FLIPGPU_OK;
+	DeviceGuard guard(f->device);
+	cudaStreamSynchronize(f->st);
+	void* ptrs[] = {f->u, f->v, f->prev_u, f->prev_v, f->p, f->s, f->dens, f->cell_type, f->cell_color, f->pos[0], f->pos[1],
+	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->slot_key, f->count,
+	                f->first, f->tile_sum, f->d_rest, f->d_margin, f->d_partials};
+	for (void* p : ptrs) if (p) cudaFree(p);
+	if (f->h_pinned) cudaFreeHost(f->h_pinned);
+	for (int i = 0; i <= FLIP_PH_COUNT; i++) if (f->ev[i]) cudaEventDestroy(f->ev[i]);
+	cudaStreamDestroy(f->st);
+	delete f;
+	return FLIPGPU_OK;
+}
+
+int flip_get_dims(FlipSim* f, FlipDims* dims) {
+	FG_CHECK(f && dims, FLIPGPU_EINVAL, "flip_get_dims: null argument");
+	*dims = f->d;
+	return FLIPGPU_OK;
+}
+
+int flip_set_num_particles(FlipSim* f, int n) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(n >= 0 && n <= f->d.max_particles, FLIPGPU_EINVAL, "num_particles %d outside [0,%d]", n, f->d.max_particles);
+	DeviceGuard guard(f->device);
+	FG_TRY(unsort(f));
+	f->d.num_particles = n;
+	f->bins_valid = false;
+	return FLIPGPU_OK;
+}
+
+int flip_upload(FlipSim* f, int field, const void* host, size_t count) {
+	FG_CHECK(f && host, FLIPGPU_EINVAL, "flip_upload: null argument");
+	FG_CHECK(field >= 0 && field < FLIP_FIELD_COUNT, FLIPGPU_EINVAL, "flip_upload: unknown field %d", field);
+	DeviceGuard guard(f->device);
+	size_t want = field_count(f, field);
+	FG_CHECK(count == want, FLIPGPU_EINVAL, "flip_upload: field %d takes %zu elements, got %zu", field, want, count);
+	void* dst = grid_field_ptr(f, field);
+	if (!dst) {
+		switch (field) {
+			case FLIP_PARTICLE_POS: FG_TRY(unsort(f)); dst = f->pos[f->cur]; f->bins_valid = false; break;
+			case FLIP_PARTICLE_VEL: FG_TRY(unsort(f)); dst = f->vel[f->cur]; break;
+			case FLIP_PARTICLE_COLOR: FG_TRY(ensure_colors(f)); FG_TRY(unsort(f)); dst = f->col[f->cur]; break;
+			case FLIP_CELL_COLOR: FG_TRY(ensure_cell_colors(f)); dst = f->cell_color; break;
+			default:
+				fg::set_error("flip_upload: field %d is derived state (hash bins) and cannot be uploaded", field);
+				return FLIPGPU_EINVAL;
+		}
+	}
+	if (count) FG_CUDA(cudaMemcpyAsync(dst, host, count * 4, cudaMemcpyHostToDevice, f->st));
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	return FLIPGPU_OK;
+}
+
+int flip_readback(FlipSim* f, int field, void* host, size_t count) {
+	FG_CHECK(f && host, FLIPGPU_EINVAL, "flip_readback: null argument");
+	FG_CHECK(field >= 0 && field < FLIP_FIELD_COUNT, FLIPGPU_EINVAL, "flip_readback: unknown field %d", field);
+	DeviceGuard guard(f->device);
+	size_t want = field_count(f, field);
+	FG_CHECK(count == want, FLIPGPU_EINVAL, "flip_readback: field %d holds %zu elements, asked for %zu", field, want, count);
+	const void* srcp = grid_field_ptr(f, field);
+	int np = f->d.num_particles, c = f->cur, n = 1 - c;
+	unsigned gr = pgrid(f);
+	if (!srcp) {
+		switch (field) {
+			case FLIP_PARTICLE_POS:
+				if (f->identity) srcp = f->pos[c];
+				else { if (np) { k_scatter_to_caller<float2, 1><<<gr, kThreads, 0, f->st>>>(np, f->orig[c], f->pos[c], f->pos[n]); f->lc.n++; } srcp = f->pos[n]; }
+				break;
+			case FLIP_PARTICLE_VEL:
+				if (f->identity) srcp = f->vel[c];
+				else { if (np) { k_scatter_to_caller<float2, 1><<<gr, kThreads, 0, f->st>>>(np, f->orig[c], f->vel[c], f->vel[n]); f->lc.n++; } srcp = f->vel[n]; }
+				break;
+			case FLIP_PARTICLE_COLOR:
+				FG_TRY(ensure_colors(f));
+				if (f->identity) srcp = f->col[c];
+				else { if (np) { k_scatter_to_caller<float, 3><<<gr, kThreads, 0, f->st>>>(np, f->orig[c], f->col[c], f->col[n]); f->lc.n++; } srcp = f->col[n]; }
+				break;
+			case FLIP_CELL_COLOR: FG_TRY(ensure_cell_colors(f)); srcp = f->cell_color; break;
+			case FLIP_NUM_CELL_PARTICLES: srcp = f->count; break;
+			case FLIP_FIRST_CELL_PARTICLE: srcp = f->first; break;
+			case FLIP_CELL_PARTICLE_IDS:
+				// before the first binning the reference array is all zero (Q4 convention)
+				if (!f->bins_valid && f->identity) { FG_CUDA(cudaMemsetAsync(f->src, 0, (size_t)np * 4, f->st)); srcp = f->src; }
+				else srcp = f->orig[c];
+				break;
+		}
+	}
+	FG_CUDA(cudaGetLastError());
+	if (count) FG_CUDA(cudaMemcpyAsync(host, srcp, count * 4, cudaMemcpyDeviceToHost, f->st));
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	return FLIPGPU_OK;
+}
+
+int flip_set_obstacle(FlipSim* f, float x, float y, float vx, float vy, float radius) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	Geo g = geo(f);
+	if (g.nx > 3 && g.ny > 3) {
+		dim3 block(32, 8), grid(cdiv(g.nx - 3, 32), cdiv(g.ny - 3, 8));
+		k_set_obstacle<<<grid, block, 0, f->st>>>(g, x, y, vx, vy, radius, f->s, f->u, f->v);
+		f->lc.n++;
+		FG_CUDA(cudaGetLastError());
+	}
+	return FLIPGPU_OK;
+}
+
+int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
+	FG_CHECK(f && sp, FLIPGPU_EINVAL, "flip_step: null argument");
+	FG_CHECK(sp->num_pressure_iters >= 0 && sp->num_particle_iters >= 0 && sp->dt > 0, FLIPGPU_EINVAL, "flip_step: bad params");
+	DeviceGuard guard(f->device);
+	const float cp = f->d.density * f->d.h / sp->dt;  // flip_fluid.h:456
+	for (int k = 0; k < n_steps; k++) {
+		if (f->timings_on) collect_timings(f);
+		if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
+		// simulate(), flip_fluid.h:566-580 (Q11: one sub-step)
+		phase_mark(f, FLIP_PH_INTEGRATE_BIN);
+		FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));
+		phase_mark(f, FLIP_PH_SEPARATE);
+		if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0));
+		phase_mark(f, FLIP_PH_COLLIDE_MARK);
+		FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
+		phase_mark(f, FLIP_PH_P2G);
+		FG_TRY(p2g(f));
+		phase_mark(f, FLIP_PH_SOLVE);
+		FG_TRY(sor_solve(sor_view(f), sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0,
+		                 sp->solver_order, f->st, &f->lc));
+		phase_mark(f, FLIP_PH_G2P);
+		FG_TRY(g2p(f, sp->flip_ratio));
+		phase_mark(f, FLIP_PH_COLORS);
+		if (sp->update_colors) FG_TRY(colors(f));
+		phase_mark(f, FLIP_PH_COUNT);
+		if (f->timings_on) f->ev_pending = true;
+	}
+	return FLIPGPU_OK;
+}
+
+int flip_phase_integrate(FlipSim* f, float dt, float gravity) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	return integrate_and_bin(f, true, false, dt, gravity);
+}
+int flip_phase_bin(FlipSim* f) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	return integrate_and_bin(f, false, true, 0.f, 0.f);
+}
+int flip_phase_separate(FlipSim* f, int num_iters, int update_colors) {
+	FG_CHECK(f && num_iters >= 0, FLIPGPU_EINVAL, "flip_phase_separate: bad argument");
+	DeviceGuard guard(f->device);
+	if (!f->bins_valid) FG_TRY(integrate_and_bin(f, false, true, 0.f, 0.f));
+	return separate(f, num_iters, update_colors != 0);
+}
+int flip_phase_collide(FlipSim* f, float ox, float oy, float ovx, float ovy, float orad) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	return collide_mark(f, true, false, ox, oy, ovx, ovy, orad);
+}
+int flip_phase_p2g(FlipSim* f) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	if (!f->bins_valid) FG_TRY(integrate_and_bin(f, false, true, 0.f, 0.f));
+	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
+	FG_TRY(collide_mark(f, false, true, 0, 0, 0, 0, 0));
+	return p2g(f);
+}
+int flip_phase_solve(FlipSim* f, int iters, float dt, float omega, int drift, int order) {
+	FG_CHECK(f && dt > 0 && iters >= 0, FLIPGPU_EINVAL, "flip_phase_solve: bad argument");
+	DeviceGuard guard(f->device);
+	// :452-454
+	FG_CUDA(cudaMemsetAsync(f->p, 0, (size_t)f->d.f_num_cells * 4, f->st));
+	FG_CUDA(cudaMemcpyAsync(f->prev_u, f->u, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
+	FG_CUDA(cudaMemcpyAsync(f->prev_v, f->v, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
+	return sor_solve(sor_view(f), iters, f->d.density * f->d.h / dt, omega, drift != 0, order, f->st, &f->lc);
+}
+int flip_phase_g2p(FlipSim* f, float flip_ratio) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	return g2p(f, flip_ratio);
+}
+int flip_phase_colors(FlipSim* f) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	return colors(f);
+}
+
+int flip_get_scalar(FlipSim* f, int which, float* out) {
+	FG_CHECK(f && out, FLIPGPU_EINVAL, "flip_get_scalar: null argument");
+	DeviceGuard guard(f->device);
+	switch (which) {
+		case FLIP_SCALAR_REST_DENSITY:
+			FG_CUDA(cudaMemcpyAsync(out, f->d_rest, 4, cudaMemcpyDeviceToHost, f->st));
+			FG_CUDA(cudaStreamSynchronize(f->st));
+			if (*out != 0.f) f->rest_seen = true;
+			return FLIPGPU_OK;
+		case FLIP_SCALAR_RESIDUAL_MAX:
+		case FLIP_SCALAR_RESIDUAL_RMS: {
+			float r2[2];
+			FG_TRY(sor_residual(sor_view(f), true, f->d_partials, kPartials, r2, f->st, &f->lc));
+			*out = which == FLIP_SCALAR_RESIDUAL_MAX ? r2[0] : r2[1];
+			return FLIPGPU_OK;
+		}
+		case FLIP_SCALAR_MAX_PUSH: {
+			int m = 0;
+			FG_CUDA(cudaMemcpyAsync(&m, f->d_margin, 4, cudaMemcpyDeviceToHost, f->st));
+			FG_CUDA(cudaStreamSynchronize(f->st));
+			*out = (float)m;
+			return FLIPGPU_OK;
+		}
+	}
+	fg::set_error("flip_get_scalar: unknown scalar %d", which);
+	return FLIPGPU_EINVAL;
+}
+
+int flip_set_rest_density(FlipSim* f, float rest) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	FG_CUDA(cudaMemcpyAsync(f->d_rest, &rest, 4, cudaMemcpyHostToDevice, f->st));
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	f->rest_seen = rest != 0.f;
+	f->h_pinned[0] = rest;
+	return FLIPGPU_OK;
+}
+
+int flip_synchronize(FlipSim* f) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	return FLIPGPU_OK;
+}
+int flip_get_stream(FlipSim* f, void** stream) {
+	FG_CHECK(f && stream, FLIPGPU_EINVAL, "null argument");
+	*stream = (void*)f->st;
+	return FLIPGPU_OK;
+}
+int flip_enable_timings(FlipSim* f, int on) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	if (!on) collect_timings(f);
+	f->timings_on = on != 0;
+	return FLIPGPU_OK;
+}
+int flip_reset_timings(FlipSim* f) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	collect_timings(f);
+	for (float& m : f->ph_ms) m = 0.f;
+	return FLIPGPU_OK;
+}
+int flip_get_timings(FlipSim* f, float* ms, int count) {
+	FG_CHECK(f && ms && count >= 0, FLIPGPU_EINVAL, "flip_get_timings: bad argument");
+	collect_timings(f);
+	for (int i = 0; i < count && i < FLIP_PH_COUNT; i++) ms[i] = f->ph_ms[i];
+	return FLIPGPU_OK;
+}
+int flip_get_launch_count(FlipSim* f, long long* launches) {
+	FG_CHECK(f && launches, FLIPGPU_EINVAL, "null argument");
+	*launches = f->lc.n;
+	return FLIPGPU_OK;
+}
+
+// flip_fluid/src/main.cpp:47-77 -- particle lattice and tank walls, host fp32 arithmetic as written there
+int flip_scene_tank(float tank_width, float tank_height, float spacing, float radius, float rel_w, float rel_h,
+                    int f_num_x, int f_num_y, float* pos, size_t pos_capacity, float* s, int* num_particles) {
+	FG_CHECK(num_particles, FLIPGPU_EINVAL, "flip_scene_tank: num_particles is null");
+	float h = spacing, r = radius;
+	float dx = 2 * r;
+	float dy = std::sqrt(3.0) / 2 * dx;  // :49 goes through double
+	int num_x = (rel_w * tank_width - 2 * h - 2 * r) / dx;
+	int num_y = (rel_h * tank_height - 2 * h - 2 * r) / dy;
+	if (num_x < 0) num_x = 0;
+	if (num_y < 0) num_y = 0;
+	long long total = (long long)num_x * num_y;
+	FG_CHECK(total < (1ll << 31), FLIPGPU_EINVAL, "flip_scene_tank: %lld particles overflow int32", total);
+	*num_particles = (int)total;
+	if (pos) {
+		FG_CHECK(pos_capacity >= 2 * (size_t)total, FLIPGPU_EINVAL, "flip_scene_tank: pos buffer too small");
+		size_t p = 0;
+		for (int i = 0; i < num_x; i++)
+			for (int j = 0; j < num_y; j++) {
+				pos[p++] = h + r + dx * i + (j % 2 == 0 ? 0 : r);
+				pos[p++] = h + r + dy * j;
+			}
+	}
+	if (s)
+		for (int j = 0; j < f_num_y; j++)
+			for (int i = 0; i < f_num_x; i++)
+				s[i + (size_t)f_num_x * j] = (i == 0 || i == f_num_x - 1 || j == 0 || j == f_num_y - 1) ? 0.f : 1.f;
+	return FLIPGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+"""GPU parity tests of the Eulerian smoke solver (pytest -m gpu) against the CPU oracle (fluid.h:98-259)."""
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as co
+import simsandgames_b200 as sg
+from tests.helpers import assert_bit_equal
+
+pytestmark = pytest.mark.gpu
+DT = 1 / 60.0
+
+
+def gpu_from(o):
+    sim = sg.FluidGPU(o.num_x - 2, o.num_y - 2, float(o.density), float(o.h))
+    assert (sim.getNumX(), sim.getNumY()) == (o.num_x, o.num_y) and sim.h1 == o.h1
+    for n in ("u", "v", "m", "pressure", "solid"):
+        sim.upload(n, getattr(o, n))
+    return sim
+
+
+@pytest.fixture(scope="module")
+def tunnel():
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    o.step(40, DT, n_steps=30)     # a developed wake
+    return o
+
+
+def test_scene_builder_matches_ui_shell():
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    sim = sg.scenes.make_wind_tunnel(96, 72)
+    for n in ("u", "v", "m", "solid"):
+        assert_bit_equal(sim.readback(n), getattr(o, n), f"scene {n}")
+
+
+def test_projection_wavefront_bit_identical(tunnel):
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    for n in ("u", "v", "m", "solid"):
+        getattr(o, n)[:] = getattr(tunnel, n)
+    sim = gpu_from(o)
+    o.solve(40, DT)
+    sim.solveIncompressibility(40, DT, solver_order=sg.LEX_WAVEFRONT)
+    for n in ("u", "v", "pressure"):
+        assert_bit_equal(sim.readback(n), getattr(o, n), f"E1 {n}")
+
+
+def test_extrapolate_and_advection_bit_exact(tunnel):
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    for n in ("u", "v", "m", "solid"):
+        getattr(o, n)[:] = getattr(tunnel, n)
+    o.solve(40, DT)
+    sim = gpu_from(o)
+    o.extrapolate(); sim.extrapolate()
+    assert_bit_equal(sim.readback("u"), o.u, "E2 u"); assert_bit_equal(sim.readback("v"), o.v, "E2 v")
+    o.advect_vel(DT); sim.advectVel(DT)
+    assert_bit_equal(sim.readback("u"), o.u, "E3 u"); assert_bit_equal(sim.readback("v"), o.v, "E3 v")
+    o.advect_smoke(DT); sim.advectSmoke(DT)
+    assert_bit_equal(sim.readback("m"), o.m, "E4 m")
+
+
+def test_whole_step_parity_mode_bit_exact():
+    """50 frames of the UI loop (fluid_ui.h:107-111) with the wavefront order: bit-identical smoke, velocity, pressure."""
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    sim = sg.scenes.make_wind_tunnel(96, 72)
+    o.step(40, DT, n_steps=50)
+    sim.step(40, DT, n_steps=50, solver_order=sg.LEX_WAVEFRONT)
+    for n in ("u", "v", "m", "pressure"):
+        assert_bit_equal(sim.readback(n), getattr(o, n), f"E5 {n}")
+
+
+def test_red_black_bounded(tunnel):
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    for n in ("u", "v", "m", "solid"):
+        getattr(o, n)[:] = getattr(tunnel, n)
+    rb = gpu_from(o)
+    gs = gpu_from(o)
+    umax = float(np.abs(o.u).max())
+    rb.solveIncompressibility(40, DT, solver_order=sg.RED_BLACK)
+    gs.solveIncompressibility(40, DT, solver_order=sg.LEX_WAVEFRONT)
+    (rb_max, rb_rms), (gs_max, gs_rms) = rb.residual(), gs.residual()
+    assert rb_rms <= 3.0 * gs_rms + 1e-6, (rb_rms, gs_rms)
+    d = max(np.abs(rb.readback("u") - gs.readback("u")).max(), np.abs(rb.readback("v") - gs.readback("v")).max())
+    assert d <= 0.5 * umax
+    # near convergence the two orders agree
+    rb.solveIncompressibility(4000, DT, solver_order=sg.RED_BLACK)
+    gs.solveIncompressibility(4000, DT, solver_order=sg.LEX_WAVEFRONT)
+    d = max(np.abs(rb.readback("u") - gs.readback("u")).max(), np.abs(rb.readback("v") - gs.readback("v")).max())
+    assert d <= 2e-3 * umax, d
+    # smoke stays a convex combination of its inputs under the production order
+    sim = sg.scenes.make_wind_tunnel(96, 72)
+    sim.step(40, DT, n_steps=100, solver_order=sg.RED_BLACK)
+    m = sim.readback("m")
+    assert np.isfinite(m).all() and m.min() >= -1e-6 and m.max() <= 1 + 1e-6
+
+
+def test_sample_field(tunnel):
+    sim = gpu_from(tunnel)
+    rng = np.random.default_rng(3)
+    xs = rng.uniform(-0.1, tunnel.num_x * float(tunnel.h) + 0.1, 500).astype(np.float32)
+    ys = rng.uniform(-0.1, tunnel.num_y * float(tunnel.h) + 0.1, 500).astype(np.float32)
+    for field in (0, 1, 2):
+        want = np.array([tunnel.sample(float(x), float(y), field) for x, y in zip(xs, ys)], np.float32)
+        assert_bit_equal(sim.sampleField(xs, ys, field), want, f"sampleField {field}")
+
+
+def test_benchmark_size_properties():
+    """BASELINE config S1: 2048^2 interior, 100 pressure iterations."""
+    sim = sg.scenes.make_wind_tunnel(2048, 2048)
+    assert (sim.getNumX(), sim.getNumY()) == (2050, 2050)
+    r0 = sim.residual()[1]
+    sim.step(100, DT, n_steps=2)
+    m = sim.readback("m"); u = sim.readback("u")
+    assert np.isfinite(m).all() and np.isfinite(u).all()
+    assert m.min() >= -1e-6 and m.max() <= 1 + 1e-6
+    sim.solveIncompressibility(100, DT)
+    assert sim.residual()[1] < r0      # projection reduces the divergence of the inflow start state

@@ -1,0 +1,423 @@
+"""GPU parity tests of the FLIP step (run on the B200 box: pytest -m gpu).
+
+Every test drives the CUDA path through the C ABI (simsandgames_b200.FlipFluidGPU -> libflipgpu.so)
+and checks it against the CPU oracle (oracle/, test infrastructure) on identical inputs.
+Protocol T0..T4 follows SURVEY 8c; tolerances are written next to each assertion.
+"""
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as co
+import simsandgames_b200 as sg
+from tests.helpers import (gpu_like, push_state, clone_oracle, assert_bit_equal, oracle_args, overlap_stats)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tank_states():
+    """Oracle (C port, pinned bit-exact to the reference) states of the default tank S0 at the start of a few steps."""
+    o, p, g = co.make_flip_scene("default", oracle_kind="port")
+    states = {}
+    done = 0
+    for target in (0, 9, 29, 60):
+        o.simulate(**p, n_steps=target - done)
+        done = target
+        states[target] = clone_oracle(o, g)
+    return states, p, g
+
+
+# ------------------------------------------------------------------ T0 / T1: per-kernel same-state replay
+@pytest.mark.parametrize("step", [0, 9, 29, 60])
+def test_integrate_and_binning_bit_exact(tank_states, step):
+    states, p, g = tank_states
+    o = clone_oracle(states[step], g)
+    sim = gpu_like(o, g)
+    o.integrate(p["dt"], p["gravity"])
+    sim.integrateParticles(p["dt"], p["gravity"])
+    P = o.num_particles
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "F1 pos")      # bit-exact (fmad off)
+    assert_bit_equal(sim.readback("particle_vel"), o.particle_vel[:2 * P], "F1 vel")
+    o.bin_particles()
+    sim.binParticles()
+    assert_bit_equal(sim.readback("num_cell_particles"), o.num_cell_particles, "F2 num_cell_particles")   # T0 bit-exact
+    assert_bit_equal(sim.readback("first_cell_particle"), o.first_cell_particle, "F2 first_cell_particle")
+    assert_bit_equal(sim.readback("cell_particle_ids"), o.cell_particle_ids[:P], "F2 cell_particle_ids")
+    # the physical re-sort is invisible through the ABI: arrays still come back in caller order
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "pos after sort")
+    assert_bit_equal(sim.readback("particle_vel"), o.particle_vel[:2 * P], "vel after sort")
+
+
+@pytest.mark.parametrize("step", [9, 60])
+def test_separation_matches_parallel_schedule_model(tank_states, step):
+    """T3 (first half): the kernel is bit-exact against the CPU model of its own schedule."""
+    states, p, g = tank_states
+    o = clone_oracle(states[step], g)
+    sim = gpu_like(o, g)
+    o.integrate(p["dt"], p["gravity"]); sim.integrateParticles(p["dt"], p["gravity"])
+    o.bin_particles(); sim.binParticles()
+    o.separate_jacobi(2, with_colors=True)
+    sim.separateParticles(2, update_colors=True)
+    P = o.num_particles
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "F3 pos vs Jacobi model")
+    assert_bit_equal(sim.readback("particle_color"), o.particle_color[:3 * P], "F3 colour vs Jacobi model")
+    # odd sweep counts take the copy-back path
+    o.separate_jacobi(1); sim.separateParticles(1)
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "F3 pos, odd sweeps")
+
+
+@pytest.mark.parametrize("step", [29, 60])
+def test_separation_statistics_vs_reference_sweep(tank_states, step):
+    """T3 (second half): distance of the parallel schedule to the reference's serial sweep, same input."""
+    states, p, g = tank_states
+    ref = clone_oracle(states[step], g)
+    sim = gpu_like(ref, g)
+    ref.integrate(p["dt"], p["gravity"]); sim.integrateParticles(p["dt"], p["gravity"])
+    ref.push_apart(2)
+    sim.pushParticlesApart(2)
+    P, r = ref.num_particles, float(ref.particle_radius)
+    a = sim.readback("particle_pos").reshape(-1, 2)
+    b = ref.particle_pos[:2 * P].reshape(-1, 2)
+    dist = np.linalg.norm(a - b, axis=1) / r
+    # measured on this scene (tests/test_separation_model.py prints the table): mean 0.10-0.16 r in the splash
+    assert dist.mean() < 0.25, dist.mean()
+    na, mina, pena = overlap_stats(a, r)
+    nb, minb, penb = overlap_stats(b, r)
+    assert abs(na - nb) <= 0.10 * nb, (na, nb)          # overlapping-pair count within 10 %
+    assert abs(pena - penb) <= 0.15 * penb, (pena, penb)  # mean penetration within 15 %
+
+
+@pytest.mark.parametrize("step", [0, 29, 60])
+def test_collide_bit_exact(tank_states, step):
+    states, p, g = tank_states
+    o = clone_oracle(states[step], g)
+    o.integrate(p["dt"], p["gravity"])
+    o.push_apart(2)
+    sim = gpu_like(o, g)
+    o.collide(p["ox"], p["oy"], 0.3, -0.2, p["orad"])
+    sim.handleParticleCollisions(p["ox"], p["oy"], 0.3, -0.2, p["orad"])
+    P = o.num_particles
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "F4 pos")
+    assert_bit_equal(sim.readback("particle_vel"), o.particle_vel[:2 * P], "F4 vel")
+
+
+@pytest.mark.parametrize("step", [0, 29, 60])
+def test_p2g_density_and_cell_types(tank_states, step):
+    states, p, g = tank_states
+    o = clone_oracle(states[step], g)
+    o.integrate(p["dt"], p["gravity"]); o.push_apart(2); o.collide(p["ox"], p["oy"], 0, 0, p["orad"])
+    sim = gpu_like(o, g)
+    if step == 0:
+        sim.particle_rest_density = 0.0
+        o.set_rest_density(0.0)
+    o.transfer(True)
+    o.update_density()
+    sim.transferVelocitiesToGrid()
+    assert_bit_equal(sim.readback("cell_type"), o.cell_type, "F5 cell_type")              # bit-exact
+    for name in ("u", "v", "particle_density"):
+        a, b = sim.readback(name), getattr(o, name)
+        scale = max(1.0, float(np.abs(b).max()))
+        # F6/F7: same per-particle arithmetic, different order of the adds into a node -> 1e-5 relative
+        assert np.abs(a - b).max() <= 1e-5 * scale, (name, np.abs(a - b).max(), scale)
+    # du == dv == particle_density in this implementation; the reference's du differs from its density only by add order
+    assert np.abs(sim.readback("du") - o.du).max() <= 1e-5 * max(1.0, float(o.du.max()))
+    rest_gpu, rest_cpu = float(sim.particle_rest_density), float(o.particle_rest_density)
+    assert abs(rest_gpu - rest_cpu) <= 1e-5 * rest_cpu, (rest_gpu, rest_cpu)               # Q14 latch
+    # prev_u/prev_v hold the post-P2G field (the copy of flip_fluid.h:453-454), p is cleared
+    assert_bit_equal(sim.readback("prev_u"), sim.readback("u"), "prev_u copy")
+    assert not sim.readback("p").any()
+
+
+def test_p2g_gather_survives_stale_bins(tank_states):
+    """Particles are binned, then moved far (a big obstacle-free push): the search margin must still find them all."""
+    states, p, g = tank_states
+    o = clone_oracle(states[60], g)
+    sim = gpu_like(o, g)
+    sim.binParticles()
+    # move every particle by up to ~3 hash cells without re-binning
+    sim.integrateParticles(0.05, 9.81)
+    o.integrate(0.05, 9.81)
+    o.transfer(True); o.update_density()
+    sim.transferVelocitiesToGrid()
+    assert sim.max_push_cells() >= 2
+    assert_bit_equal(sim.readback("cell_type"), o.cell_type, "cell_type")
+    a, b = sim.readback("particle_density"), o.particle_density
+    assert np.abs(a - b).max() <= 1e-5 * float(b.max())
+    assert abs(float(a.sum()) - o.num_particles) <= 1e-4 * o.num_particles  # every particle splats total weight 1
+
+
+@pytest.mark.parametrize("step", [0, 29, 60])
+def test_g2p_bit_exact(tank_states, step):
+    states, p, g = tank_states
+    o = clone_oracle(states[step], g)
+    o.integrate(p["dt"], p["gravity"]); o.push_apart(2); o.collide(p["ox"], p["oy"], 0, 0, p["orad"])
+    o.transfer(True); o.update_density(); o.solve(50, p["dt"], 1.9, True)
+    sim = gpu_like(o, g)
+    o.transfer(False, 0.9)
+    sim.transferVelocitiesToParticles(0.9)
+    P = o.num_particles
+    assert_bit_equal(sim.readback("particle_vel"), o.particle_vel[:2 * P], "F8 vel")  # gather: same arithmetic, bit-exact
+
+
+@pytest.mark.parametrize("step", [0, 29, 60])
+def test_solver_wavefront_bit_identical(tank_states, step):
+    """F9 parity mode: the anti-diagonal schedule reproduces the lexicographic loop order bit for bit."""
+    states, p, g = tank_states
+    o = clone_oracle(states[step], g)
+    o.integrate(p["dt"], p["gravity"]); o.push_apart(2); o.collide(p["ox"], p["oy"], 0, 0, p["orad"])
+    o.transfer(True); o.update_density()
+    sim = gpu_like(o, g)
+    o.solve(50, p["dt"], 1.9, True)
+    sim.solveIncompressibility(50, p["dt"], 1.9, True, solver_order=sg.LEX_WAVEFRONT)
+    for name in ("u", "v", "p", "prev_u", "prev_v"):
+        assert_bit_equal(sim.readback(name), getattr(o, name), f"F9 wavefront {name}")
+
+
+def _cpu_residual(o, drift=True):
+    nx, ny = o.f_num_x, o.f_num_y
+    u = o.u.reshape(ny, nx).astype(np.float64); v = o.v.reshape(ny, nx).astype(np.float64)
+    s = o.s.reshape(ny, nx); ct = o.cell_type.reshape(ny, nx); dens = o.particle_density.reshape(ny, nx)
+    div = u[1:-1, 2:] - u[1:-1, 1:-1] + v[2:, 1:-1] - v[1:-1, 1:-1]
+    ssum = s[1:-1, :-2] + s[1:-1, 2:] + s[:-2, 1:-1] + s[2:, 1:-1]
+    rest = float(o.particle_rest_density)
+    if drift and rest > 0:
+        div = div - np.maximum(dens[1:-1, 1:-1] - rest, 0)
+    mask = (ct[1:-1, 1:-1] == 0) & (ssum != 0)
+    d = div[mask]
+    return float(np.abs(d).max()), float(np.sqrt((d * d).mean()))
+
+
+@pytest.mark.parametrize("step", [0, 60])
+def test_solver_red_black_bounded_against_gauss_seidel(tank_states, step):
+    """T2: red-black and lexicographic Gauss-Seidel are consistent orderings of the same SOR splitting and share
+    the fixed point u*: ||u_RB-u_GS|| <= ||u_RB-u*|| + ||u_GS-u*||.  Checked three ways: residual after the
+    reference's iteration count, distance between the two after 50 iterations, and agreement near convergence."""
+    states, p, g = tank_states
+    base = clone_oracle(states[step], g)
+    base.integrate(p["dt"], p["gravity"]); base.push_apart(2); base.collide(p["ox"], p["oy"], 0, 0, p["orad"])
+    base.transfer(True); base.update_density()
+    umax = max(float(np.abs(base.u).max()), float(np.abs(base.v).max()), 1e-3)
+
+    def run(iters, order):
+        sim = gpu_like(base, g)
+        sim.solveIncompressibility(iters, p["dt"], 1.9, True, solver_order=order)
+        return sim
+
+    gs50 = clone_oracle(base, g); gs50.solve(50, p["dt"], 1.9, True)
+    rb50 = run(50, sg.RED_BLACK)
+    gs_max, gs_rms = _cpu_residual(gs50)
+    rb_max, rb_rms = rb50.residual()
+    assert rb_rms <= 3.0 * gs_rms + 1e-6, (rb_rms, gs_rms)      # residual after the reference's 50 iterations <= 3x
+    assert rb_max <= 4.0 * gs_max + 1e-6, (rb_max, gs_max)
+    # the library's residual reduction agrees with a float64 numpy evaluation of the same field
+    o2 = clone_oracle(base, g); o2.u[:] = rb50.readback("u"); o2.v[:] = rb50.readback("v")
+    chk_max, chk_rms = _cpu_residual(o2)
+    assert abs(chk_max - rb_max) <= 1e-4 * max(1.0, chk_max) and abs(chk_rms - rb_rms) <= 1e-4 * max(1.0, chk_rms)
+    d50 = max(np.abs(rb50.readback("u") - gs50.u).max(), np.abs(rb50.readback("v") - gs50.v).max())
+    assert d50 <= 0.5 * umax, (d50, umax)                       # SURVEY probe: 0.25 of max|u| at 50 iterations
+    # near convergence both orders reach the same field (fp32 floor)
+    gs_conv = clone_oracle(base, g); gs_conv.solve(3000, p["dt"], 1.9, True)
+    rb_conv = run(3000, sg.RED_BLACK)
+    dconv = max(np.abs(rb_conv.readback("u") - gs_conv.u).max(), np.abs(rb_conv.readback("v") - gs_conv.v).max())
+    assert dconv <= 2e-3 * umax, (dconv, umax)
+
+
+# ------------------------------------------------------------------ T4: trajectories
+def test_short_trajectory_parity_mode(tank_states):
+    """5 whole steps, wavefront solver, separation off: only the P2G add order differs -> positions within 1e-5."""
+    states, p, g = tank_states
+    o = clone_oracle(states[29], g)
+    sim = gpu_like(o, g)
+    pp = dict(p, separate_particles=False)
+    o.simulate(**pp, n_steps=5)
+    kw = {k: v for k, v in oracle_to_product(pp).items()}
+    sim.simulate(**kw, n_steps=5, solver_order=sg.LEX_WAVEFRONT, update_colors=True)
+    P = o.num_particles
+    dpos = np.abs(sim.readback("particle_pos") - o.particle_pos[:2 * P]).max()
+    dvel = np.abs(sim.readback("particle_vel") - o.particle_vel[:2 * P]).max()
+    assert dpos <= 1e-5 * 4.0, dpos     # domain width 4
+    assert dvel <= 2e-3, dvel
+    assert_bit_equal(sim.readback("cell_type"), o.cell_type, "cell_type after 5 steps")
+    dcol = np.abs(sim.readback("cell_color") - o.cell_color).max()
+    assert dcol <= 1e-3, dcol
+
+
+def oracle_to_product(p):
+    m = {"ox": "obstacle_x", "oy": "obstacle_y", "ovx": "obstacle_vel_x", "ovy": "obstacle_vel_y", "orad": "obstacle_radius"}
+    return {m.get(k, k): v for k, v in p.items()}
+
+
+def test_short_trajectory_performance_mode(tank_states):
+    """5 whole steps with the production settings (red-black + parallel separation): pointwise within 1 r."""
+    states, p, g = tank_states
+    o = clone_oracle(states[60], g)
+    sim = gpu_like(o, g)
+    o.simulate(**p, n_steps=5)
+    sim.simulate(**oracle_to_product(p), n_steps=5, solver_order=sg.RED_BLACK, update_colors=False)
+    P, r = o.num_particles, float(o.particle_radius)
+    d = np.linalg.norm((sim.readback("particle_pos") - o.particle_pos[:2 * P]).reshape(-1, 2), axis=1) / r
+    assert d.mean() <= 1.0, d.mean()
+    assert np.quantile(d, 0.99) <= 6.0, np.quantile(d, 0.99)
+
+
+def test_long_run_invariants_default_tank():
+    """1000 steps of S0 on the GPU vs 1000 steps of the oracle: chaotic, so compare invariants."""
+    o, p, g = co.make_flip_scene("default", oracle_kind="port")
+    sim, kw, g2 = sg.scenes.make_flip_tank("default")
+    assert g2["max_particles"] == g["max_particles"] == 19092
+    P = o.num_particles
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "scene particles")
+    assert_bit_equal(sim.readback("s"), o.s, "scene s")
+    h, r = float(o.h), float(o.particle_radius)
+    for chunk in range(4):
+        o.simulate(**p, n_steps=250)
+        sim.simulate(**kw, n_steps=250, update_colors=False)
+        pos = sim.readback("particle_pos").reshape(-1, 2)
+        assert np.isfinite(pos).all()
+        assert pos[:, 0].min() >= h + r - 1e-6 and pos[:, 0].max() <= h * (o.f_num_x - 1) - r + 1e-6
+        assert pos[:, 1].min() >= h + r - 1e-6 and pos[:, 1].max() <= h * (o.f_num_y - 1) - r + 1e-6
+        my_gpu, my_cpu = float(pos[:, 1].mean()), float(o.particle_pos[1:2 * P:2].mean())
+        assert abs(my_gpu - my_cpu) <= 3e-2 * 3.0, (chunk, my_gpu, my_cpu)   # mean height, domain height 3
+    rest_gpu, rest_cpu = float(sim.particle_rest_density), float(o.particle_rest_density)
+    assert abs(rest_gpu - rest_cpu) <= 1e-5 * rest_cpu     # latched at step 1: 3.130026 on S0
+    # kinetic energy envelope: both pools have come to rest to the same degree
+    ke_gpu = float((sim.readback("particle_vel").astype(np.float64) ** 2).sum() / P)
+    ke_cpu = float((o.particle_vel[:2 * P].astype(np.float64) ** 2).sum() / P)
+    assert ke_gpu <= 4.0 * ke_cpu + 1e-3, (ke_gpu, ke_cpu)
+    na, _, pena = overlap_stats(pos, r)
+    nb, _, penb = overlap_stats(o.particle_pos[:2 * P], r)
+    assert abs(na - nb) <= 0.15 * nb, (na, nb)
+
+
+def test_run_to_run_bit_stable():
+    """The whole step is deterministic: no float atomics anywhere (north_star: atomic-free P2G)."""
+    outs = []
+    for _ in range(2):
+        sim, kw, g = sg.scenes.make_flip_tank("default")
+        sim.simulate(**kw, n_steps=40, update_colors=True)
+        outs.append((sim.readback("particle_pos"), sim.readback("u"), sim.readback("particle_color")))
+    for a, b in zip(*outs):
+        assert_bit_equal(a, b, "run-to-run")
+
+
+def test_set_obstacle_matches_ui_shell(tank_states):
+    states, p, g = tank_states
+    o = clone_oracle(states[29], g)
+    sim = gpu_like(o, g)
+    x, y, vx, vy, rad = 1.7, 1.1, 0.5, -0.25, 0.2
+    inside, rng = co.flip_obstacle_mask(o.f_num_x, o.f_num_y, o.h, x, y, rad)
+    s = o.s.reshape(o.f_num_y, o.f_num_x).copy(); u = o.u.reshape(o.f_num_y, o.f_num_x).copy(); v = o.v.reshape(o.f_num_y, o.f_num_x).copy()
+    s[rng] = 1; s[inside] = 0
+    jj, ii = np.nonzero(inside)
+    u[jj, ii] = vx; u[jj, ii + 1] = vx; v[jj, ii] = vy; v[jj + 1, ii] = vy
+    sim.set_obstacle(x, y, vx, vy, rad)
+    assert_bit_equal(sim.readback("s"), s, "setObstacle s")
+    assert_bit_equal(sim.readback("u"), u, "setObstacle u")
+    assert_bit_equal(sim.readback("v"), v, "setObstacle v")
+
+
+def test_colors_phase(tank_states):
+    states, p, g = tank_states
+    o = clone_oracle(states[60], g)
+    sim = gpu_like(o, g)
+    o.particle_colors(); o.cell_colors()
+    sim.updateColors()
+    P = o.num_particles
+    assert_bit_equal(sim.readback("particle_color"), o.particle_color[:3 * P], "F10 particle colours")
+    assert_bit_equal(sim.readback("cell_color"), o.cell_color, "F10 cell colours")
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_and_single_particle():
+    sim = sg.FlipFluidGPU(1000.0, 1.0, 1.0, 0.1, 0.03, 16)
+    s = np.ones((sim.f_num_y, sim.f_num_x), np.float32); s[0] = 0; s[-1] = 0; s[:, 0] = 0; s[:, -1] = 0
+    sim.upload("s", s)
+    kw = dict(dt=1 / 60, gravity=9.81, flip_ratio=.9, num_pressure_iters=10, num_particle_iters=2, over_relaxation=1.9,
+              compensate_drift=True, separate_particles=True, obstacle_x=0, obstacle_y=0, obstacle_vel_x=0,
+              obstacle_vel_y=0, obstacle_radius=0)
+    sim.simulate(**kw, n_steps=3)                      # zero particles: nothing to do, nothing to crash
+    assert sim.readback("particle_pos").size == 0
+    assert (sim.readback("cell_type").reshape(s.shape)[s == 1] == 1).all()   # all air
+    sim.num_particles = 1
+    sim.upload("particle_pos", np.array([0.5, 0.5], np.float32))
+    o = co.FlipOracle(1000.0, 1.0, 1.0, 0.1, 0.03, 16, kind="port")
+    o.s[:] = s.reshape(-1); o.set_num_particles(1); o.particle_pos[:2] = [0.5, 0.5]
+    o.simulate(**oracle_args(kw), n_steps=20)
+    sim.simulate(**kw, n_steps=20, solver_order=sg.LEX_WAVEFRONT)
+    assert np.abs(sim.readback("particle_pos") - o.particle_pos[:2]).max() <= 1e-6
+    assert_bit_equal(sim.readback("cell_particle_ids"), o.cell_particle_ids[:1], "ids")
+
+
+def test_particles_outside_domain_and_crowded_cell():
+    """Clamped hash keys (flip_fluid.h:174-175), many particles in one cell, positions outside the tank."""
+    rng = np.random.default_rng(7)
+    o = co.FlipOracle(1000.0, 2.0, 1.5, 0.05, 0.012, 4000, kind="port")
+    P = 4000
+    pos = rng.uniform(-0.3, 2.3, (P, 2)).astype(np.float32)
+    pos[:, 1] = rng.uniform(-0.3, 1.8, P).astype(np.float32)
+    pos[:300] = np.float32([0.7, 0.7]) + rng.normal(0, 1e-3, (300, 2)).astype(np.float32)   # crowd one cell
+    pos[300:310] = pos[300]                                                                   # exact duplicates (d==0)
+    o.set_num_particles(P); o.particle_pos[:] = pos.reshape(-1)
+    o.particle_vel[:] = rng.normal(0, 1, 2 * P).astype(np.float32)
+    s = np.ones((o.f_num_y, o.f_num_x), np.float32); s[0] = 0; s[-1] = 0; s[:, 0] = 0; s[:, -1] = 0
+    o.s[:] = s.reshape(-1)
+    g = dict(density=1000.0, width=2.0, height=1.5, spacing=0.05, radius=0.012, max_particles=P)
+    sim = gpu_like(o, g)
+    o.bin_particles(); sim.binParticles()
+    assert_bit_equal(sim.readback("num_cell_particles"), o.num_cell_particles, "counts")
+    assert_bit_equal(sim.readback("first_cell_particle"), o.first_cell_particle, "firsts")
+    assert_bit_equal(sim.readback("cell_particle_ids"), o.cell_particle_ids[:P], "ids")
+    o.separate_jacobi(2); sim.separateParticles(2)
+    assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], "separation with outsiders")
+    # P2G with positions outside the grid (clamped onto border nodes by the stencil)
+    o.transfer(True); o.update_density()
+    sim.transferVelocitiesToGrid()
+    assert_bit_equal(sim.readback("cell_type"), o.cell_type, "cell_type")
+    for name in ("u", "v", "particle_density"):
+        a, b = sim.readback(name), getattr(o, name)
+        assert np.abs(a - b).max() <= 2e-5 * max(1.0, float(np.abs(b).max())), name
+    o.transfer(False, 0.9); sim.transferVelocitiesToParticles(0.9)
+    assert np.abs(sim.readback("particle_vel") - o.particle_vel[:2 * P]).max() <= 1e-4
+
+
+def test_abi_error_paths():
+    sim = sg.FlipFluidGPU(1000.0, 1.0, 1.0, 0.1, 0.03, 8)
+    with pytest.raises(sg.FlipGpuError):
+        sim.num_particles = 9                      # beyond max_particles
+    with pytest.raises(sg.FlipGpuError):
+        sim.upload("u", np.zeros(3, np.float32))   # wrong element count
+    with pytest.raises(sg.FlipGpuError):
+        sim.upload("cell_particle_ids", np.zeros(0, np.int32))  # derived state
+    with pytest.raises(sg.FlipGpuError):
+        sg.FlipFluidGPU(1000.0, 1.0, 1.0, 0.0, 0.03, 8)
+
+
+# ------------------------------------------------------------------ size-independent properties at benchmark scale
+@pytest.mark.parametrize("N", [1024, 4096])
+def test_large_scene_properties(N):
+    """Synthetic dam-break (SURVEY S2 rule).  N=4096 is the BASELINE config: 4096^2 cells, 64 264 080 particles."""
+    sim, kw, g = sg.scenes.make_flip_tank("synthetic", N=N)
+    P = sim.num_particles
+    if N == 4096:
+        assert (sim.f_num_x, sim.f_num_y, P) == (4096, 4096, 64264080)
+    pos0 = sim.readback("particle_pos")
+    sim.simulate(**kw, n_steps=2, update_colors=False)
+    cnt = sim.readback("num_cell_particles"); first = sim.readback("first_cell_particle"); ids = sim.readback("cell_particle_ids")
+    assert int(cnt.sum(dtype=np.int64)) == P and first[-1] == P and first[0] == 0
+    assert np.array_equal(np.diff(first.astype(np.int64)), cnt)                      # exclusive starts of the counts
+    seen = np.zeros(P, np.uint8); seen[ids] = 1
+    assert seen.all()                                                                # ids is a permutation
+    same_cell = np.ones(P - 1, bool); same_cell[first[1:-1][(first[1:-1] > 0) & (first[1:-1] < P)] - 1] = False
+    assert (np.diff(ids)[same_cell] < 0).all()                                       # descending inside every cell (Q7)
+    pos = sim.readback("particle_pos").reshape(-1, 2)
+    h, r = float(sim.h), float(sim.particle_radius)
+    assert np.isfinite(pos).all()
+    assert pos.min() >= h + r - 1e-6 and pos[:, 0].max() <= h * (sim.f_num_x - 1) - r + 1e-6
+    dens = sim.readback("particle_density")
+    assert abs(float(dens.sum(dtype=np.float64)) - P) <= 1e-5 * P                    # every particle splats weight 1
+    ct = sim.readback("cell_type")
+    assert set(np.unique(ct)) <= {0, 1, 2} and (ct == 0).sum() > 0.3 * 0.48 * ct.size
+    mx, rms = sim.residual()
+    assert np.isfinite(mx) and rms < 1.0
+    # moved, but by less than a few cells per step (CFL-matched dt)
+    assert 0 < np.abs(pos.reshape(-1) - pos0).max() < 8 * h
