@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native grid-fluid step.
+
+Workload (BASELINE.json configs[2], the config the north_star target is quoted on):
+  flip_fluid synthetic dam-break, 4096^2 grid, 64 264 080 particles, simulate(dt, 9.81, .9, 50, 2, 1.9, true, true, ...)
+  one "step" = one FlipFluid::simulate (flip_fluid.h:560-581) with the render-state colour kernels off.
+Metric: particle-steps/s (whole job).  cell-updates/s of the pressure solve and the roofline are reported beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          product arm (CUDA through the C ABI)
+  python bench.py --impl reference ...                         the reference's own CPU code on the host cores
+Under torchrun (N>1) every rank owns one GPU; timing = CUDA events on the library's stream, bracketed by a
+barrier + synchronize, max over ranks.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "flip_particle_steps_per_s"
+UNIT = "particle-steps/s"
+BENCH_N = 4096
+WORKLOAD = "flip_fluid synthetic dam-break 4096^2 grid, 64264080 particles, 50 SOR iters, 2 separation sweeps (BASELINE configs[2])"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def cpu_sample_size(steps, warmup):
+    """Grid size of the bounded CPU sample: the same dam-break rule, sized so (steps+warmup) CPU steps take ~2 minutes
+    (the serial reference needs ~4.4 s/step at 1024^2 and ~70 s/step at 4096^2)."""
+    budget_s = 120.0
+    n = 1024.0 * math.sqrt(budget_s / (4.4 * max(1, steps + warmup)))
+    return int(max(256, min(1024, (int(n) // 128) * 128)))
+
+
+def run_cpu_reference(n_sample, steps, warmup):
+    """The reference's CPU step (oracle/_ref = unmodified flip_fluid.h; else the C port) on a bounded sample."""
+    from oracle import cpu_oracle as co
+    kind = co.best_kind("flip")
+    o, p, g = co.make_flip_scene("synthetic", N=n_sample, oracle_kind=kind)
+    P = o.num_particles
+    if warmup:
+        o.simulate(**p, n_steps=warmup)
+    t0 = time.perf_counter()
+    ph = o.simulate(**p, n_steps=steps, timed=True)
+    dt = time.perf_counter() - t0
+    interior = (o.f_num_x - 2) * (o.f_num_y - 2)
+    return dict(kind="reference" if kind == "ref" else "port", particles=P, grid=n_sample, seconds=dt, steps=steps,
+                value=P * steps / dt, cell_updates_per_s=interior * p["num_pressure_iters"] * steps / (ph[5] * 1e-9),
+                phase_share={k: round(v / sum(ph), 4) for k, v in zip(
+                    ("integrate", "pushApart", "collide", "p2g", "density", "solve", "g2p", "colours"), ph)})
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n_sample = cpu_sample_size(args.steps, args.warmup)
+    r = run_cpu_reference(n_sample, args.steps, args.warmup)
+    sample = (f"same dam-break rule at {n_sample}^2 cells / {r['particles']} particles, {args.steps} steps after {args.warmup} warm-up, "
+              f"1 thread (the reference is serial: no threads/OpenMP/SIMD in first-party code)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "timing": "host steady clock around the reference's simulate()"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": sample,
+                         "cell_updates_per_s": r["cell_updates_per_s"], "phase_share": r["phase_share"],
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def product_arm(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import simsandgames_b200 as sg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    N = args.grid
+    sim, kw, geo = sg.scenes.make_flip_tank("synthetic", N=N, device=local_rank)
+    P, nx, ny = sim.num_particles, sim.f_num_x, sim.f_num_y
+    iters = kw["num_pressure_iters"]
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        sim.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput ("value"): K x flip_step, state resident in HBM
+    sim.simulate(**kw, n_steps=args.warmup, update_colors=False)
+    barrier()
+    sim.enable_timings(True)
+    sim.reset_timings()
+    launches0 = sim.launch_count
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.simulate(**kw, n_steps=args.steps, update_colors=False)
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launch_count - launches0
+    phases = sim.timings()
+    sim.enable_timings(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): per step, the caller's per-frame writes go H2D
+    #      (the s field that FluidUI::setObstacle rewrites every frame, main.cpp:106-122) and the array the caller
+    #      reads every frame comes back D2H (particle_pos, main.cpp:173-176), in caller particle order.
+    e2e_steps = max(2, min(args.steps, 5))
+    h_s = torch.from_numpy(sim.readback("s")).pin_memory()
+    h_pos = torch.empty(2 * P, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    for _ in range(e2e_steps):
+        sim.upload_from("s", h_s.data_ptr(), h_s.numel())
+        sim.simulate(**kw, n_steps=1, update_colors=False)
+        sim.readback_into("particle_pos", h_pos.data_ptr(), h_pos.numel())
+    g1.record(stream)
+    sim.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    e2e_ms = max(g0.elapsed_time(g1), 1e3 * wall)  # the calls are synchronous: device span vs host wall, whichever is longer
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+    assert bool(torch.isfinite(h_pos[:1024]).all())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    s_per_step = ms_max * 1e-3 / args.steps
+    interior = (nx - 2) * (ny - 2)
+    C = nx * ny
+    # roofline of the dominant kernel = one red-black colour pass of the SOR solve
+    solve_ms_per_step = phases["solve"] / args.steps
+    n_solver_launches = 2 * iters
+    launch_s = solve_ms_per_step * 1e-3 / n_solver_launches
+    alg_bytes_per_launch = 36.0 * interior / 2.0          # 36 B per cell-update x half the interior per colour pass
+    achieved = alg_bytes_per_launch / launch_s / 1e9
+    step_bytes = 140.0 * P + (96.0 + 36.0 * iters) * C      # SURVEY 8d whole-step formula
+    line = {
+        "metric": METRIC, "value": world * P / s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD if N == BENCH_N else f"flip_fluid synthetic dam-break {N}^2 (non-default --grid)",
+                   "grid": [nx, ny], "particles_per_gpu": P, "pressure_iters": iters, "separation_sweeps": 2,
+                   "solver_order": "red_black", "colours": "off (render state, SURVEY 8d)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent tanks, one per GPU (no halo exchange yet)",
+                   "l2": "working set ~4.7 GB per step >> 126 MB L2 (no flush needed)",
+                   "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
+                   "samples": clk["samples"], "power_w_max": clk.get("power_w_max")},
+        "e2e": {"value": world * P * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_s.numel() * 4),
+                "d2h_bytes_per_step": int(h_pos.numel() * 4), "steps": e2e_steps,
+                "what": "flip_upload(s) + flip_step + flip_readback(particle_pos, caller order), pinned host buffers"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "sor_rb_pass_kernel (one colour pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches},
+        "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / s_per_step / 1e9, "unit": "GB/s",
+                          "frac_of_measured": step_bytes / s_per_step / 1e9 / peak, "frac_of_8TBs": step_bytes / s_per_step / 8e12,
+                          "formula": "140*P + (96+36*iters)*C  (SURVEY 8d)"},
+        "cell_updates_per_s": world * interior * iters / (solve_ms_per_step * 1e-3),
+        "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = 1024
+        r = run_cpu_reference(n_sample, 3, 0)
+        line["cpu_baseline"] = {
+            "value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"],
+            "sample": f"same dam-break rule at {n_sample}^2 cells / {r['particles']} particles, 3 steps, 1 thread of {os.cpu_count()} host CPUs "
+                      f"({r['seconds']:.1f} s; the reference is serial)",
+            "cell_updates_per_s": r["cell_updates_per_s"], "phase_share": r["phase_share"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="flipgpu", choices=["flipgpu", "reference"])
+    ap.add_argument("--grid", type=int, default=BENCH_N, help="cells per side of the synthetic dam-break (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        product_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -573,8 +573,10 @@ struct FlipSim {
 	bool rest_seen = false;
 	bool timings_on = false;
 	float ph_ms[FLIP_PH_COUNT] = {0};
-	cudaEvent_t ev[FLIP_PH_COUNT + 1] = {nullptr};
-	bool ev_pending = false;
+	static constexpr int kEvRing = 32;  // per-step event sets; a slot is only waited on when it is reused 32 steps later
+	cudaEvent_t ev[kEvRing][FLIP_PH_COUNT + 1] = {{nullptr}};
+	bool ev_pending[kEvRing] = {false};
+	int ev_slot = 0;
 	LaunchCounter lc;
 };
 
@@ -633,16 +635,19 @@ int unsort(FlipSim* f) {
 }
 
 void phase_mark(FlipSim* f, int idx) {
-	if (f->timings_on) cudaEventRecord(f->ev[idx], f->st);
+	if (f->timings_on) cudaEventRecord(f->ev[f->ev_slot][idx], f->st);
 }
-void collect_timings(FlipSim* f) {
-	if (!f->ev_pending) return;
-	cudaEventSynchronize(f->ev[FLIP_PH_COUNT]);
+void collect_slot(FlipSim* f, int slot) {
+	if (!f->ev_pending[slot]) return;
+	cudaEventSynchronize(f->ev[slot][FLIP_PH_COUNT]);
 	for (int i = 0; i < FLIP_PH_COUNT; i++) {
 		float ms = 0.f;
-		if (cudaEventElapsedTime(&ms, f->ev[i], f->ev[i + 1]) == cudaSuccess) f->ph_ms[i] += ms;
+		if (cudaEventElapsedTime(&ms, f->ev[slot][i], f->ev[slot][i + 1]) == cudaSuccess) f->ph_ms[i] += ms;
 	}
-	f->ev_pending = false;
+	f->ev_pending[slot] = false;
+}
+void collect_timings(FlipSim* f) {
+	for (int s = 0; s < FlipSim::kEvRing; s++) collect_slot(f, s);
 }
 
 // F2: counting sort into hash-cell order.  keys/count must already hold this step's histogram.
@@ -891,7 +896,8 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	FG_CUDA(cudaMalloc(&f->d_partials, (3 * kPartials + 8) * 4));
 	FG_CUDA(cudaMallocHost(&f->h_pinned, 64));
 	f->h_pinned[0] = 0.f;
-	for (int i = 0; i <= FLIP_PH_COUNT; i++) FG_CUDA(cudaEventCreate(&f->ev[i]));
+	for (int r = 0; r < FlipSim::kEvRing; r++)
+		for (int i = 0; i <= FLIP_PH_COUNT; i++) FG_CUDA(cudaEventCreate(&f->ev[r][i]));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	*out = f;
 	return FLIPGPU_OK;
@@ -906,7 +912,8 @@ int flip_destroy(FlipSim* f) {
 	                f->first, f->tile_sum, f->d_rest, f->d_margin, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
-	for (int i = 0; i <= FLIP_PH_COUNT; i++) if (f->ev[i]) cudaEventDestroy(f->ev[i]);
+	for (int r = 0; r < FlipSim::kEvRing; r++)
+		for (int i = 0; i <= FLIP_PH_COUNT; i++) if (f->ev[r][i]) cudaEventDestroy(f->ev[r][i]);
 	cudaStreamDestroy(f->st);
 	delete f;
 	return FLIPGPU_OK;
@@ -1010,7 +1017,7 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 	DeviceGuard guard(f->device);
 	const float cp = f->d.density * f->d.h / sp->dt;  // flip_fluid.h:456
 	for (int k = 0; k < n_steps; k++) {
-		if (f->timings_on) collect_timings(f);
+		if (f->timings_on) collect_slot(f, f->ev_slot);
 		if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
 		// simulate(), flip_fluid.h:566-580 (Q11: one sub-step)
 		phase_mark(f, FLIP_PH_INTEGRATE_BIN);
@@ -1029,7 +1036,10 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		phase_mark(f, FLIP_PH_COLORS);
 		if (sp->update_colors) FG_TRY(colors(f));
 		phase_mark(f, FLIP_PH_COUNT);
-		if (f->timings_on) f->ev_pending = true;
+		if (f->timings_on) {
+			f->ev_pending[f->ev_slot] = true;
+			f->ev_slot = (f->ev_slot + 1) % FlipSim::kEvRing;
+		}
 	}
 	return FLIPGPU_OK;
 }

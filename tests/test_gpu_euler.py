@@ -68,23 +68,35 @@ def test_whole_step_parity_mode_bit_exact():
 
 
 def test_red_black_bounded(tunnel):
+    """T2 for E1.  Red-black and lexicographic Gauss-Seidel are consistent orderings of one SOR splitting and share
+    the fixed point u*; so ||u_RB-u_GS|| <= ||u_RB-u*|| + ||u_GS-u*||.  u* = the wavefront order run to the fp32 floor."""
     o = co.make_euler_scene(96, 72, oracle_kind="port")
     for n in ("u", "v", "m", "solid"):
         getattr(o, n)[:] = getattr(tunnel, n)
-    rb = gpu_from(o)
-    gs = gpu_from(o)
     umax = float(np.abs(o.u).max())
-    rb.solveIncompressibility(40, DT, solver_order=sg.RED_BLACK)
-    gs.solveIncompressibility(40, DT, solver_order=sg.LEX_WAVEFRONT)
-    (rb_max, rb_rms), (gs_max, gs_rms) = rb.residual(), gs.residual()
-    assert rb_rms <= 3.0 * gs_rms + 1e-6, (rb_rms, gs_rms)
-    d = max(np.abs(rb.readback("u") - gs.readback("u")).max(), np.abs(rb.readback("v") - gs.readback("v")).max())
-    assert d <= 0.5 * umax
-    # near convergence the two orders agree
-    rb.solveIncompressibility(4000, DT, solver_order=sg.RED_BLACK)
-    gs.solveIncompressibility(4000, DT, solver_order=sg.LEX_WAVEFRONT)
-    d = max(np.abs(rb.readback("u") - gs.readback("u")).max(), np.abs(rb.readback("v") - gs.readback("v")).max())
-    assert d <= 2e-3 * umax, d
+    star = gpu_from(o)
+    star.solveIncompressibility(6000, DT, solver_order=sg.LEX_WAVEFRONT)
+    us, vs = star.readback("u"), star.readback("v")
+    rb_star = gpu_from(o)
+    rb_star.solveIncompressibility(6000, DT, solver_order=sg.RED_BLACK)
+    d = max(np.abs(rb_star.readback("u") - us).max(), np.abs(rb_star.readback("v") - vs).max())
+    assert d <= 2e-5 * umax, d                       # same fixed point (measured 1.7e-5 absolute, |u|max 3.8)
+
+    def err(sim):
+        return max(np.abs(sim.readback("u") - us).max(), np.abs(sim.readback("v") - vs).max())
+
+    for iters in (40, 100):                          # 40 = the reference's count (fluid_ui.h:107)
+        rb, gs = gpu_from(o), gpu_from(o)
+        rb.solveIncompressibility(iters, DT, solver_order=sg.RED_BLACK)
+        gs.solveIncompressibility(iters, DT, solver_order=sg.LEX_WAVEFRONT)
+        e_rb, e_gs = err(rb), err(gs)
+        assert e_rb <= 2.0 * e_gs + 1e-5, (iters, e_rb, e_gs)          # measured ratio 1.0-1.4
+        dist = max(np.abs(rb.readback("u") - gs.readback("u")).max(), np.abs(rb.readback("v") - gs.readback("v")).max())
+        assert dist <= e_rb + e_gs + 1e-5, (iters, dist, e_rb, e_gs)   # the explicit GS->RB bound
+        (rb_max, rb_rms), (gs_max, gs_rms) = rb.residual(), gs.residual()
+        assert rb_max <= 3.0 * gs_max + 1e-6, (iters, rb_max, gs_max)  # measured 1.4-1.6x
+        # rms is dominated by the checkerboard the last black half-sweep leaves on the red cells (measured 8.6-13x)
+        assert rb_rms <= 20.0 * gs_rms + 1e-6, (iters, rb_rms, gs_rms)
     # smoke stays a convex combination of its inputs under the production order
     sim = sg.scenes.make_wind_tunnel(96, 72)
     sim.step(40, DT, n_steps=100, solver_order=sg.RED_BLACK)
@@ -106,10 +118,10 @@ def test_benchmark_size_properties():
     """BASELINE config S1: 2048^2 interior, 100 pressure iterations."""
     sim = sg.scenes.make_wind_tunnel(2048, 2048)
     assert (sim.getNumX(), sim.getNumY()) == (2050, 2050)
-    r0 = sim.residual()[1]
     sim.step(100, DT, n_steps=2)
     m = sim.readback("m"); u = sim.readback("u")
     assert np.isfinite(m).all() and np.isfinite(u).all()
     assert m.min() >= -1e-6 and m.max() <= 1 + 1e-6
+    r0 = sim.residual()[1]
     sim.solveIncompressibility(100, DT)
-    assert sim.residual()[1] < r0      # projection reduces the divergence of the inflow start state
+    assert sim.residual()[1] < r0      # projection reduces the divergence left by advection
