@@ -72,7 +72,9 @@ typedef enum {
 
 typedef enum {
 	FLIP_SOLVER_RED_BLACK = 0,     /* performance order (north_star); bounded against the reference order */
-	FLIP_SOLVER_LEX_WAVEFRONT = 1  /* anti-diagonal schedule, bit-identical to the loop order of flip_fluid.h:458-494 */
+	FLIP_SOLVER_LEX_WAVEFRONT = 1, /* the reference's lexicographic loop order (flip_fluid.h:458-494) as a blocked
+	                                  anti-diagonal wavefront in shared memory: bit-identical u,v,p */
+	FLIP_SOLVER_LEX_DIAGONAL = 2   /* same order, unblocked one-diagonal-per-grid-sync kernel (cross-check / non-binary s) */
 } FlipSolverOrder;
 
 /* the 13 arguments of FlipFluid::simulate (flip_fluid.h:560-565) + two switches */
@@ -89,8 +91,7 @@ typedef struct {
 typedef enum {
 	FLIP_SCALAR_REST_DENSITY = 0, /* particle_rest_density (flip_fluid.h:44,321-332) */
 	FLIP_SCALAR_RESIDUAL_MAX,     /* max |div| over cells the solver updates, incl. drift term */
-	FLIP_SCALAR_RESIDUAL_RMS,
-	FLIP_SCALAR_MAX_PUSH          /* largest particle displacement since the last binning, in hash cells */
+	FLIP_SCALAR_RESIDUAL_RMS
 } FlipScalar;
 
 /* phases of simulate() for flip_get_timings, ms accumulated since flip_reset_timings */

@@ -17,6 +17,7 @@ _LIB = None
 
 RED_BLACK = 0
 LEX_WAVEFRONT = 1
+LEX_DIAGONAL = 2
 
 FLIP_FIELDS = {  # name -> (enum value, numpy dtype)   order == FlipField in flipgpu.h
     "u": (0, np.float32), "v": (1, np.float32), "du": (2, np.float32), "dv": (3, np.float32),
@@ -218,11 +219,6 @@ class FlipFluidGPU:
         _check(self._lib.flip_get_scalar(self._h, 1, C.byref(mx)), "flip_get_scalar")
         _check(self._lib.flip_get_scalar(self._h, 2, C.byref(rms)), "flip_get_scalar")
         return float(mx.value), float(rms.value)
-
-    def max_push_cells(self):
-        out = C.c_float()
-        _check(self._lib.flip_get_scalar(self._h, 3, C.byref(out)), "flip_get_scalar")
-        return int(out.value)
 
     def synchronize(self):
         _check(self._lib.flip_synchronize(self._h), "flip_synchronize")

@@ -67,8 +67,14 @@ struct SorGrid {
 	                       // association order of the divergence (flip_fluid.h:476 / fluid.h:122-123)
 };
 
-int sor_solve(const SorGrid& g, int iters, float cp, float omega, bool drift, int order, cudaStream_t st,
-              LaunchCounter* lc);
+struct SorWorkspace;  // plan + per-cell constants of the blocked-wavefront solver (sor_tiled.cu)
+void sor_workspace_free(SorWorkspace* w);
+int sor_solve_tiled(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
+                    LaunchCounter* lc);
+// order: FlipSolverOrder.  s_binary: every s is 0 or 1 (required by the blocked kernel's 1-byte cell code;
+// otherwise LEX_WAVEFRONT falls back to the unblocked diagonal kernel, same results).
+int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,
+              cudaStream_t st, LaunchCounter* lc);
 int sor_residual(const SorGrid& g, bool drift, float* d_partials, int n_partials, float* h_out2, cudaStream_t st,
                  LaunchCounter* lc);
 

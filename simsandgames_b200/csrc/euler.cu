@@ -122,6 +122,7 @@ struct EulerSim {
 	int* cell_type = nullptr;  // derived
 	bool coeff_dirty = true;
 	float* d_partials = nullptr;
+	SorWorkspace* ws = nullptr;
 	LaunchCounter lc;
 };
 
@@ -164,7 +165,7 @@ int project(EulerSim* e, int iters, float dt, int order) {
 	FG_TRY(refresh_coeff(e));
 	FG_CUDA(cudaMemsetAsync(e->pressure, 0, (size_t)e->d.num_cells * 4, e->st));  // fluid.h:101-103
 	float cp = e->d.density * e->d.h / dt;                                          // fluid.h:100
-	return sor_solve(esor(e), iters, cp, 1.9f, false, order, e->st, &e->lc);
+	return sor_solve(&e->ws, esor(e), iters, cp, 1.9f, false, order, true, e->st, &e->lc);
 }
 int extrapolate(EulerSim* e) {
 	EGeo g = egeo(e);
@@ -236,6 +237,7 @@ int euler_destroy(EulerSim* e) {
 	cudaStreamSynchronize(e->st);
 	void* ptrs[] = {e->u, e->v, e->new_u, e->new_v, e->pressure, e->m, e->new_m, e->s, e->solid, e->cell_type, e->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
+	sor_workspace_free(e->ws);
 	cudaStreamDestroy(e->st);
 	delete e;
 	return FLIPGPU_OK;

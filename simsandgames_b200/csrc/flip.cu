@@ -230,18 +230,16 @@ __global__ void __launch_bounds__(kThreads) k_fixup_cells(int n_cells, const int
 	}
 }
 
-// physical reorder into hash-cell order; also records each slot's bin (for the P2G search margin)
+// physical reorder into hash-cell order
 template <bool COLORS>
 __global__ void __launch_bounds__(kThreads) k_reorder(Geo g, const int* __restrict__ src, const float2* __restrict__ pos_in,
                                                       const float2* __restrict__ vel_in, const float* __restrict__ col_in,
                                                       float2* __restrict__ pos_out, float2* __restrict__ vel_out,
-                                                      float* __restrict__ col_out, int* __restrict__ slot_key) {
+                                                      float* __restrict__ col_out) {
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
 		int k = src[t];
-		float2 p = pos_in[k];
-		pos_out[t] = p;
+		pos_out[t] = pos_in[k];
 		vel_out[t] = vel_in[k];
-		slot_key[t] = hash_cell(g, p.x, p.y);
 		if (COLORS) {
 			col_out[3 * (size_t)t] = col_in[3 * (size_t)k];
 			col_out[3 * (size_t)t + 1] = col_in[3 * (size_t)k + 1];
@@ -323,18 +321,17 @@ __global__ void __launch_bounds__(kThreads) k_cell_type_from_s(int n, const floa
 }
 
 // ------------------------------------------------------------------ F4 + F5 marking
-// handleParticleCollisions (flip_fluid.h:254-289) fused with the fluid-cell marking of :352-359 and
-// with the bookkeeping the gather-form P2G needs: how far (in hash cells) a particle now sits from the
-// bin it was sorted into.
+// handleParticleCollisions (flip_fluid.h:254-289) fused with the fluid-cell marking of :352-359 and with
+// the key + histogram of the second (index-only) counting sort: particles by the BASE CELL (x0,y0) of their
+// bilinear stencil, taken from the final positions of this step.  That list is what makes the P2G a gather.
 template <bool COLLIDE>
 __global__ void __launch_bounds__(kThreads) k_collide_mark(Geo g, float2* __restrict__ pos, float2* __restrict__ vel, float ox,
                                                            float oy, float ovx, float ovy, float orad,
-                                                           int* __restrict__ cell_type, const int* __restrict__ slot_key,
-                                                           int* __restrict__ margin) {
+                                                           int* __restrict__ cell_type, int* __restrict__ gkeys,
+                                                           int* __restrict__ gcount) {
 	const float md = g.r + orad, md2 = md * md;
 	const float min_x = g.h + g.r, max_x = g.h * (float)(g.nx - 1) - g.r;
 	const float min_y = g.h + g.r, max_y = g.h * (float)(g.ny - 1) - g.r;
-	int m = 0;
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
 		float2 p = pos[t];
 		if (COLLIDE) {
@@ -353,31 +350,47 @@ __global__ void __launch_bounds__(kThreads) k_collide_mark(Geo g, float2* __rest
 			int yi = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
 			int c = xi + g.nx * yi;
 			if (cell_type[c] == AIR_CELL) cell_type[c] = FLUID_CELL;  // all racing writers store the same value
-		}
-		if (slot_key) {
-			int cx, cy;
-			hash_cell(g, p.x, p.y, &cx, &cy);
-			int key = slot_key[t];
-			int kx = key % g.pnx, ky = key / g.pnx;
-			m = max(m, max(abs(cx - kx), abs(cy - ky)));
+			// base cell of the stencil, exactly as :301-308 (clamped position, cell-centred offset)
+			float x = clampf(p.x, g.h, g.xmax_c), y = clampf(p.y, g.h, g.ymax_c);
+			int x0 = clampi((int)(g.inv_h * (x - g.h2)), 0, g.nx - 1), y0 = clampi((int)(g.inv_h * (y - g.h2)), 0, g.ny - 1);
+			int key = x0 + g.nx * y0;
+			gkeys[t] = key;
+			atomicAdd(gcount + key, 1);  // integer histogram: order-independent
 		}
 	}
-	if (slot_key) {
-		m = warp_max(m);
-		if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(margin, m);
+}
+
+// fill of the index-only sort (slots claimed in any order) ...
+__global__ void __launch_bounds__(kThreads) k_fill_grid(int np, const int* __restrict__ gkeys, int* __restrict__ gfirst,
+                                                        int* __restrict__ gidx) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x)
+		gidx[atomicSub(gfirst + gkeys[t], 1) - 1] = t;
+}
+// ... then every cell's list is sorted by slot number, which fixes the order of the float adds of the gather
+__global__ void __launch_bounds__(kThreads) k_fixup_grid(int n_cells, const int* __restrict__ gcount,
+                                                         const int* __restrict__ gfirst, int* __restrict__ gidx) {
+	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+		int n = gcount[c];
+		if (n < 2) continue;
+		int b = gfirst[c];
+		for (int i = 1; i < n; i++) {
+			int v = gidx[b + i], j = i - 1;
+			while (j >= 0 && gidx[b + j] > v) { gidx[b + j + 1] = gidx[b + j]; j--; }
+			gidx[b + j + 1] = v;
+		}
 	}
 }
 
 // ------------------------------------------------------------------ F6 + F7: sort-ordered, atomic-free P2G
 // transferVelocities(true) splat + normalise + solid restore (flip_fluid.h:362-403,432-446) and
-// updateParticleDensity (:292-319) in GATHER form: one thread per grid node walks the hash rows that
-// can hold a contributing particle (contiguous slot ranges, because particles are sorted in pIX order)
-// and accumulates its own node in slot order -- no atomics, run-to-run bit-stable.  The per-particle
-// arithmetic is the reference's; only the order of the adds into a node differs (slot order instead of
-// caller order).  du, dv and particle_density are one array here: the reference computes the same
-// weights three times (bit-equal except aliased border cells).
-__global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict__ first, const float2* __restrict__ pos,
-                                                    const float2* __restrict__ vel, const int* __restrict__ margin_p,
+// updateParticleDensity (:292-319) in GATHER form: one thread per grid node reads the particle lists of the
+// (up to) four base cells whose stencils reach it -- cells (i-1..i, j-1..j); the two cells of a row are one
+// contiguous range of the list -- and accumulates its own node in list order: no atomics, run-to-run
+// bit-stable.  The per-particle arithmetic is the reference's; only the order of the adds into a node
+// differs (slot order instead of caller order).  du, dv and particle_density are one array here: the
+// reference computes the same weights three times (bit-equal except aliased border cells).
+__global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict__ gfirst, const int* __restrict__ gidx,
+                                                    const float2* __restrict__ pos, const float2* __restrict__ vel,
                                                     const int* __restrict__ cell_type, float* __restrict__ u,
                                                     float* __restrict__ v, float* __restrict__ prev_u,
                                                     float* __restrict__ prev_v, float* __restrict__ dens,
@@ -385,22 +398,12 @@ __global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	int j = blockIdx.y * blockDim.y + threadIdx.y;
 	if (i >= g.nx || j >= g.ny) return;
-	const int margin = *margin_p;
-	// positions whose base cell x0 is i-1 or i lie in [h(i-1)+h2, h(i+1)+h2); pad for fp32 rounding
-	float pad = 1e-5f * fmaxf(g.xmax_c, g.ymax_c);
-	float xlo = g.h * (float)(i - 1) + g.h2 - pad, xhi = g.h * (float)(i + 1) + g.h2 + pad;
-	float ylo = g.h * (float)(j - 1) + g.h2 - pad, yhi = g.h * (float)(j + 1) + g.h2 + pad;
-	int cx0 = clampi((int)(xlo * g.p_inv) - margin, 0, g.pnx - 1), cx1 = clampi((int)(xhi * g.p_inv) + margin, 0, g.pnx - 1);
-	int cy0 = clampi((int)(ylo * g.p_inv) - margin, 0, g.pny - 1), cy1 = clampi((int)(yhi * g.p_inv) + margin, 0, g.pny - 1);
-	// positions outside the grid are clamped onto the border nodes by the stencil (:301-302), wherever they were binned
-	if (i <= 1) cx0 = 0;
-	if (i >= g.nx - 2) cx1 = g.pnx - 1;
-	if (j <= 1) cy0 = 0;
-	if (j >= g.ny - 2) cy1 = g.pny - 1;
 	float su = 0.f, sv = 0.f, sw = 0.f;
-	for (int cy = cy0; cy <= cy1; cy++) {
-		int a = first[cx0 + g.pnx * cy], b = first[cx1 + g.pnx * cy + 1];
-		for (int t = a; t < b; t++) {
+	int cx0 = max(i - 1, 0);
+	for (int cy = max(j - 1, 0); cy <= j; cy++) {
+		int a = gfirst[cx0 + g.nx * cy], b = gfirst[i + g.nx * cy + 1];
+		for (int k = a; k < b; k++) {
+			int t = gidx[k];
 			float2 pp = pos[t];
 			Stencil st = make_stencil(g, pp.x, pp.y);
 			bool mx0 = st.x0 == i, mx1 = st.x1 == i, my0 = st.y0 == j, my1 = st.y1 == j;
@@ -563,11 +566,13 @@ struct FlipSim {
 	float* col[2] = {nullptr, nullptr};  // lazily allocated
 	int* orig[2] = {nullptr, nullptr};   // caller index per slot; orig[cur] doubles as cell_particle_ids
 	int cur = 0;
-	int *keys = nullptr, *src = nullptr, *slot_key = nullptr, *count = nullptr, *first = nullptr, *tile_sum = nullptr;
+	int *keys = nullptr, *src = nullptr, *count = nullptr, *first = nullptr, *tile_sum = nullptr;
+	int *gcount = nullptr, *gfirst = nullptr;  // particles per stencil base cell (P2G gather lists; keys/src are reused for them)
 	float* d_rest = nullptr;   // device scalar particle_rest_density
-	int* d_margin = nullptr;   // device scalar, P2G search margin in hash cells
 	float* d_partials = nullptr;
 	float* h_pinned = nullptr;  // [0] rest mirror
+	SorWorkspace* ws = nullptr;
+	bool s_binary = true;       // every s[] is 0 or 1 (tracked on upload)
 	bool identity = true;       // slot order == caller order
 	bool bins_valid = false;
 	bool rest_seen = false;
@@ -650,23 +655,28 @@ void collect_timings(FlipSim* f) {
 	for (int s = 0; s < FlipSim::kEvRing; s++) collect_slot(f, s);
 }
 
+// inclusive running sum of count[0..n) into first[0..n), first[n] = total (flip_fluid.h:180-186)
+void running_sum(FlipSim* f, const int* count, int n, int* first) {
+	int tiles = (int)cdiv((size_t)n, kScanTile);
+	k_scan_tile_sums<<<tiles, kScanThreads, 0, f->st>>>(count, n, f->tile_sum);
+	k_scan_tile_offsets<<<1, 1024, 0, f->st>>>(f->tile_sum, tiles);
+	k_scan_tiles<<<tiles, kScanThreads, 0, f->st>>>(count, n, f->tile_sum, first);
+	f->lc.n += 3;
+}
+
 // F2: counting sort into hash-cell order.  keys/count must already hold this step's histogram.
 int bin_from_histogram(FlipSim* f) {
 	Geo g = geo(f);
 	int Hc = f->d.p_num_cells, np = g.np;
-	int tiles = (int)cdiv((size_t)Hc, kScanTile);
-	k_scan_tile_sums<<<tiles, kScanThreads, 0, f->st>>>(f->count, Hc, f->tile_sum);
-	k_scan_tile_offsets<<<1, 1024, 0, f->st>>>(f->tile_sum, tiles);
-	k_scan_tiles<<<tiles, kScanThreads, 0, f->st>>>(f->count, Hc, f->tile_sum, f->first);
-	f->lc.n += 3;
+	running_sum(f, f->count, Hc, f->first);
 	int c = f->cur, n = 1 - c;
 	if (np > 0) {
 		k_fill<<<pgrid(f), kThreads, 0, f->st>>>(np, f->keys, f->orig[c], f->first, f->src, f->orig[n]);
 		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count, f->first, f->src, f->orig[n]);
 		if (f->col[0])
-			k_reorder<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], f->slot_key);
+			k_reorder<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n]);
 		else
-			k_reorder<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr, f->slot_key);
+			k_reorder<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr);
 		f->lc.n += 3;
 		f->cur = n;
 		f->identity = false;
@@ -719,18 +729,25 @@ int separate(FlipSim* f, int iters, bool colors) {
 
 int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad) {
 	Geo g = geo(f);
-	int c = f->cur;
+	int c = f->cur, C = f->d.f_num_cells;
 	if (mark) {
-		k_cell_type_from_s<<<wave_grid(f->d.f_num_cells, kThreads), kThreads, 0, f->st>>>(f->d.f_num_cells, f->s, f->cell_type);
+		k_cell_type_from_s<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->s, f->cell_type);
 		f->lc.n++;
-		FG_CUDA(cudaMemsetAsync(f->d_margin, 0, sizeof(int), f->st));
+		FG_CUDA(cudaMemsetAsync(f->gcount, 0, (size_t)C * 4, f->st));
 	}
 	if (g.np > 0) {
 		int* ct = mark ? f->cell_type : nullptr;
-		const int* sk = mark ? f->slot_key : nullptr;
-		if (collide) k_collide_mark<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, sk, f->d_margin);
-		else k_collide_mark<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, sk, f->d_margin);
+		if (collide) k_collide_mark<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, f->keys, f->gcount);
+		else k_collide_mark<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, f->keys, f->gcount);
 		f->lc.n++;
+	}
+	if (mark) {  // index-only counting sort by stencil base cell: gidx (= src) lists the slots of every grid cell
+		running_sum(f, f->gcount, C, f->gfirst);
+		if (g.np > 0) {
+			k_fill_grid<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->keys, f->gfirst, f->src);
+			k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount, f->gfirst, f->src);
+			f->lc.n += 2;
+		}
 	}
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
@@ -741,7 +758,7 @@ int p2g(FlipSim* f) {
 	int c = f->cur;
 	dim3 block(32, 8);
 	dim3 grid(cdiv(g.nx, block.x), cdiv(g.ny, block.y));
-	k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->first, f->pos[c], f->vel[c], f->d_margin, f->cell_type, f->u, f->v,
+	k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
 	                                        f->prev_u, f->prev_v, f->dens, f->p);
 	f->lc.n++;
 	if (!f->rest_seen) {
@@ -882,17 +899,16 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	}
 	FG_CUDA(cudaMalloc(&f->keys, M * 4));
 	FG_CUDA(cudaMalloc(&f->src, M * 4));
-	FG_CUDA(cudaMalloc(&f->slot_key, M * 4));
+	FG_CUDA(cudaMalloc(&f->gcount, C * 4));
+	FG_CUDA(cudaMalloc(&f->gfirst, (C + 1) * 4));
 	FG_CUDA(cudaMalloc(&f->count, H * 4));
 	FG_CUDA(cudaMalloc(&f->first, (H + 1) * 4));
 	FG_CUDA(cudaMemsetAsync(f->count, 0, H * 4, f->st));
 	FG_CUDA(cudaMemsetAsync(f->first, 0, (H + 1) * 4, f->st));
 	FG_CUDA(cudaMemsetAsync(f->src, 0, M * 4, f->st));
-	FG_CUDA(cudaMalloc(&f->tile_sum, (size_t)(cdiv(H, kScanTile) + 1) * 4));
+	FG_CUDA(cudaMalloc(&f->tile_sum, (size_t)(cdiv(std::max(H, C), kScanTile) + 1) * 4));
 	FG_CUDA(cudaMalloc(&f->d_rest, 4));
-	FG_CUDA(cudaMalloc(&f->d_margin, 4));
 	FG_CUDA(cudaMemsetAsync(f->d_rest, 0, 4, f->st));
-	FG_CUDA(cudaMemsetAsync(f->d_margin, 0, 4, f->st));
 	FG_CUDA(cudaMalloc(&f->d_partials, (3 * kPartials + 8) * 4));
 	FG_CUDA(cudaMallocHost(&f->h_pinned, 64));
 	f->h_pinned[0] = 0.f;
@@ -908,10 +924,11 @@ int flip_destroy(FlipSim* f) {
 	DeviceGuard guard(f->device);
 	cudaStreamSynchronize(f->st);
 	void* ptrs[] = {f->u, f->v, f->prev_u, f->prev_v, f->p, f->s, f->dens, f->cell_type, f->cell_color, f->pos[0], f->pos[1],
-	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->slot_key, f->count,
-	                f->first, f->tile_sum, f->d_rest, f->d_margin, f->d_partials};
+	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->gcount, f->gfirst, f->count,
+	                f->first, f->tile_sum, f->d_rest, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
+	sor_workspace_free(f->ws);
 	for (int r = 0; r < FlipSim::kEvRing; r++)
 		for (int i = 0; i <= FLIP_PH_COUNT; i++) if (f->ev[r][i]) cudaEventDestroy(f->ev[r][i]);
 	cudaStreamDestroy(f->st);
@@ -952,6 +969,12 @@ int flip_upload(FlipSim* f, int field, const void* host, size_t count) {
 				fg::set_error("flip_upload: field %d is derived state (hash bins) and cannot be uploaded", field);
 				return FLIPGPU_EINVAL;
 		}
+	}
+	if (field == FLIP_S) {  // the blocked solver packs s into one bit per neighbour; remember whether that is exact
+		const float* hs = (const float*)host;
+		bool bin = true;
+		for (size_t i = 0; i < count && bin; i++) bin = hs[i] == 0.f || hs[i] == 1.f;
+		f->s_binary = bin;
 	}
 	if (count) FG_CUDA(cudaMemcpyAsync(dst, host, count * 4, cudaMemcpyHostToDevice, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
@@ -1029,8 +1052,8 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		phase_mark(f, FLIP_PH_P2G);
 		FG_TRY(p2g(f));
 		phase_mark(f, FLIP_PH_SOLVE);
-		FG_TRY(sor_solve(sor_view(f), sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0,
-		                 sp->solver_order, f->st, &f->lc));
+		FG_TRY(sor_solve(&f->ws, sor_view(f), sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0,
+		                 sp->solver_order, f->s_binary, f->st, &f->lc));
 		phase_mark(f, FLIP_PH_G2P);
 		FG_TRY(g2p(f, sp->flip_ratio));
 		phase_mark(f, FLIP_PH_COLORS);
@@ -1068,7 +1091,6 @@ int flip_phase_collide(FlipSim* f, float ox, float oy, float ovx, float ovy, flo
 int flip_phase_p2g(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	DeviceGuard guard(f->device);
-	if (!f->bins_valid) FG_TRY(integrate_and_bin(f, false, true, 0.f, 0.f));
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
 	FG_TRY(collide_mark(f, false, true, 0, 0, 0, 0, 0));
 	return p2g(f);
@@ -1080,7 +1102,7 @@ int flip_phase_solve(FlipSim* f, int iters, float dt, float omega, int drift, in
 	FG_CUDA(cudaMemsetAsync(f->p, 0, (size_t)f->d.f_num_cells * 4, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->prev_u, f->u, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->prev_v, f->v, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
-	return sor_solve(sor_view(f), iters, f->d.density * f->d.h / dt, omega, drift != 0, order, f->st, &f->lc);
+	return sor_solve(&f->ws, sor_view(f), iters, f->d.density * f->d.h / dt, omega, drift != 0, order, f->s_binary, f->st, &f->lc);
 }
 int flip_phase_g2p(FlipSim* f, float flip_ratio) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
@@ -1107,13 +1129,6 @@ int flip_get_scalar(FlipSim* f, int which, float* out) {
 			float r2[2];
 			FG_TRY(sor_residual(sor_view(f), true, f->d_partials, kPartials, r2, f->st, &f->lc));
 			*out = which == FLIP_SCALAR_RESIDUAL_MAX ? r2[0] : r2[1];
-			return FLIPGPU_OK;
-		}
-		case FLIP_SCALAR_MAX_PUSH: {
-			int m = 0;
-			FG_CUDA(cudaMemcpyAsync(&m, f->d_margin, 4, cudaMemcpyDeviceToHost, f->st));
-			FG_CUDA(cudaStreamSynchronize(f->st));
-			*out = (float)m;
 			return FLIPGPU_OK;
 		}
 	}

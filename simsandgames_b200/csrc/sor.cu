@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(256) sor_wavefront_kernel(SorGrid g, int iters
 	}
 }
 
-int sor_solve(const SorGrid& g, int iters, float cp, float omega, bool drift, int order, cudaStream_t st,
-              LaunchCounter* lc) {
+int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,
+              cudaStream_t st, LaunchCounter* lc) {
 	if (iters <= 0 || g.nf < 3 || g.ns < 3) return FLIPGPU_OK;
 	bool use_drift = drift && g.density && g.rest;
-	if (order == FLIP_SOLVER_LEX_WAVEFRONT) {
+	if (order == FLIP_SOLVER_LEX_WAVEFRONT && s_binary && ws) return sor_solve_tiled(ws, g, iters, cp, omega, drift, st, lc);
+	if (order == FLIP_SOLVER_LEX_WAVEFRONT || order == FLIP_SOLVER_LEX_DIAGONAL) {
 		int dev = 0, sms = 0, per_sm = 0;
 		FG_CUDA(cudaGetDevice(&dev));
 		FG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

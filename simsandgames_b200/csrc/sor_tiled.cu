@@ -1,0 +1,256 @@
+// Blocked-wavefront Gauss-Seidel SOR: the reference's lexicographic sweep order
+// (flip_fluid.h:458-494 / fluid.h:106-138), bit for bit, staged through shared memory with
+// temporal blocking, as ONE persistent kernel per solve.
+//
+// Why this order and not plain red-black: with the reference's iteration count the lexicographic sweep
+// carries pressure information across the whole grid in the sweep direction every iteration; red-black
+// moves it two cells per iteration and, at the reference's 50 iterations, leaves tall liquid columns
+// unsupported (the dam-break configs blow up within ~20 steps, profiles/r1_stability.md).  The
+// anti-diagonal wavefront is the parallel schedule that IS the lexicographic order: a cell shares faces
+// only with its four edge neighbours, so all cells with i+j = const are independent and iteration k+1 may
+// trail iteration k by two diagonals.
+//
+// Blocking.  Let (F,S) be interior cell coordinates along the fast/slow storage axes.  The iteration
+// space (F,S,k) is cut into tiles  { (F0-k+a, S0-k+b, q*Kc+k) : 0<=a,b<T, 0<=k<Kc }  -- squares of side T
+// skewed by one cell per iteration.  In the skewed coordinates every dependency of (a,b,k) points to
+// (a-1,b,.), (a,b-1,.) or (a-1,b-1,k-1), so
+//   * inside a tile, ALL Kc iterations of local diagonal a+b = t are independent: 2T-1 block-wide steps
+//     do T*T*Kc cell updates out of shared memory;
+//   * between tiles the dependencies are (I-1,J,q), (I,J-1,q) and (I+1,J+1,q-1): tiles are handed out in
+//     wave order I+J+3q from an atomic counter and wait on completion flags of earlier tiles only.
+// HBM traffic per solve is ~(1+2Kc/T) grid sweeps per chunk of Kc iterations instead of Kc sweeps, with
+// no redundant computation (skewing, not halo recompute).  Compiled with -fmad=false.
+#include <vector>
+#include "common.cuh"
+
+namespace fg {
+
+constexpr int kTile = 32;        // T: one warp spans a tile row of the skewed square
+constexpr int kMaxChunk = 16;    // Kc <= kMaxChunk <= T
+constexpr int kBoxW = kTile + kMaxChunk;  // even: lane stride kBoxW-1 is odd -> conflict-free diagonals
+
+struct TiledArgs {
+	int nf, ns;
+	float* vel_f;
+	float* vel_s;
+	float* p;
+	const unsigned char* code;  // bit0 active, bit1..4 = s != 0 at fast-, fast+, slow-, slow+ neighbour
+	const float* drift;         // max(0, density-rest) when drift compensation applies, else nullptr
+	const int4* tiles;          // (I, J, q, kq) in wave order
+	int n_tiles, ni, nj, kc;
+	int* flags;                 // flags[(q*nj+J)*ni+I] == epoch  <=> tile complete
+	int* counter;
+	int epoch;
+	float cp, omega;
+};
+
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
+	while (*((volatile const int*)flag) != epoch) __nanosleep(64);
+}
+
+template <bool XFAST, bool DRIFT>
+__global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledArgs A) {
+	__shared__ float s_vf[kBoxW * kBoxW];
+	__shared__ float s_vs[kBoxW * kBoxW];
+	__shared__ float s_p[kBoxW * kBoxW];
+	__shared__ float s_dr[DRIFT ? kBoxW * kBoxW : 1];
+	__shared__ unsigned char s_code[kBoxW * kBoxW];
+	__shared__ int s_tile;
+	const int tid = threadIdx.y * kTile + threadIdx.x;
+	const int nthreads = kTile * blockDim.y;
+	const int nf = A.nf, ns = A.ns;
+	for (;;) {
+		if (tid == 0) s_tile = atomicAdd(A.counter, 1);
+		__syncthreads();
+		const int ti = s_tile;
+		if (ti >= A.n_tiles) return;
+		const int4 tl = A.tiles[ti];
+		const int I = tl.x, J = tl.y, q = tl.z, kq = tl.w;
+		if (tid == 0) {
+			if (I > 0) wait_flag(A.flags + (q * A.nj + J) * A.ni + I - 1, A.epoch);
+			if (J > 0) wait_flag(A.flags + (q * A.nj + J - 1) * A.ni + I, A.epoch);
+			if (q > 0) wait_flag(A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1), A.epoch);
+			__threadfence();
+		}
+		__syncthreads();
+		const int F0 = 1 + I * kTile, S0 = 1 + J * kTile;
+		const int FB = F0 - A.kc + 1, SB = S0 - A.kc + 1;  // box origin (cells FB..FB+kBoxW-1)
+		// ---- stage the box (L2-coherent loads: the producers are other CTAs of this launch)
+		for (int e = tid; e < kBoxW * kBoxW; e += nthreads) {
+			int lf = e % kBoxW, ls = e / kBoxW;
+			int F = FB + lf, S = SB + ls;
+			float vf = 0.f, vs = 0.f, pp = 0.f, dr = 0.f;
+			unsigned char cd = 0;
+			if (F >= 0 && F < nf && S >= 0 && S < ns) {
+				size_t c = (size_t)F + (size_t)nf * S;
+				vf = __ldcg(A.vel_f + c); vs = __ldcg(A.vel_s + c); pp = __ldcg(A.p + c);
+				cd = A.code[c];
+				if (DRIFT) dr = A.drift[c];
+			}
+			s_vf[e] = vf; s_vs[e] = vs; s_p[e] = pp; s_code[e] = cd;
+			if (DRIFT) s_dr[e] = dr;
+		}
+		__syncthreads();
+		// ---- 2T-1 local diagonals; on each, every iteration of the chunk in parallel
+		const int a = threadIdx.x;
+		for (int t = 0; t < 2 * kTile - 1; t++) {
+			int b = t - a;
+			if (b >= 0 && b < kTile) {
+				for (int k = threadIdx.y; k < kq; k += blockDim.y) {
+					int F = F0 - k + a, S = S0 - k + b;
+					if (F < 1 || F > nf - 2 || S < 1 || S > ns - 2) continue;
+					int e = (F - FB) + kBoxW * (S - SB);
+					unsigned cd = s_code[e];
+					if (!(cd & 1u)) continue;
+					float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
+					float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
+					float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+					float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[e + kBoxW];
+					float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
+					if (DRIFT) {
+						float compression = s_dr[e];
+						if (compression > 0.f) div -= compression;
+					}
+					float pv = -div / ssum;
+					pv *= A.omega;
+					s_p[e] += A.cp * pv;
+					s_vf[e] = vfc - sfm * pv;
+					s_vf[e + 1] = vfp + sfp * pv;
+					s_vs[e] = vsc - ssm * pv;
+					s_vs[e + kBoxW] = vsp + ssp * pv;
+				}
+			}
+			__syncthreads();
+		}
+		// ---- write back exactly what this tile owns: cells it updated, plus their high-side faces
+		for (int e = tid; e < kBoxW * kBoxW; e += nthreads) {
+			int lf = e % kBoxW, ls = e / kBoxW;
+			int F = FB + lf, S = SB + ls;
+			if (F < 1 || F > nf - 1 || S < 1 || S > ns - 1) continue;
+			int x = F - F0, y = S - S0;
+			// cell (x,y) is visited at iterations k in [max(0,-x,-y), min(kq-1, T-1-x, T-1-y)]
+			auto visited = [&](int xx, int yy) {
+				int lo = max(0, max(-xx, -yy)), hi = min(kq - 1, min(kTile - 1 - xx, kTile - 1 - yy));
+				return lo <= hi;
+			};
+			bool own = visited(x, y) && F <= nf - 2 && S <= ns - 2;
+			bool from_f = visited(x - 1, y) && F - 1 >= 1 && S <= ns - 2;  // high-side face of the fast- neighbour
+			bool from_s = visited(x, y - 1) && S - 1 >= 1 && F <= nf - 2;  // high-side face of the slow- neighbour
+			size_t c = (size_t)F + (size_t)nf * S;
+			if (own) __stcg(A.p + c, s_p[e]);
+			if (own || from_f) __stcg(A.vel_f + c, s_vf[e]);
+			if (own || from_s) __stcg(A.vel_s + c, s_vs[e]);
+		}
+		__threadfence();
+		__syncthreads();
+		if (tid == 0) *((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
+	}
+}
+
+// per-solve constants of every cell: the neighbour-openness code and the drift term
+__global__ void __launch_bounds__(256) sor_prep_kernel(SorGrid g, bool drift, unsigned char* __restrict__ code,
+                                                       float* __restrict__ drift_out) {
+	float rest = (drift && g.rest) ? *g.rest : 0.f;
+	size_t n = (size_t)g.nf * g.ns;
+	for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+		int a = (int)(c % g.nf), b = (int)(c / g.nf);
+		unsigned cd = 0;
+		float dr = 0.f;
+		if (a >= 1 && a <= g.nf - 2 && b >= 1 && b <= g.ns - 2 && g.cell_type[c] == FLUID_CELL) {
+			unsigned m = (g.s[c - 1] != 0.f ? 2u : 0u) | (g.s[c + 1] != 0.f ? 4u : 0u) | (g.s[c - g.nf] != 0.f ? 8u : 0u) |
+			             (g.s[c + g.nf] != 0.f ? 16u : 0u);
+			if (m) cd = m | 1u;
+			if (drift && rest > 0.f) {
+				float compression = g.density[c] - rest;
+				if (compression > 0.f) dr = compression;
+			}
+		}
+		code[c] = (unsigned char)cd;
+		if (drift_out) drift_out[c] = dr;
+	}
+}
+
+struct SorWorkspace {
+	int nf = 0, ns = 0, iters = 0, kc = 0, ni = 0, nj = 0, nq = 0, n_tiles = 0, epoch = 0;
+	unsigned char* code = nullptr;
+	float* drift = nullptr;
+	int4* tiles = nullptr;
+	int* flags = nullptr;
+	int* counter = nullptr;
+	int sms = 0;
+};
+
+void sor_workspace_free(SorWorkspace* w) {
+	if (!w) return;
+	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter);
+	delete w;
+}
+
+static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
+	if (w->nf != g.nf || w->ns != g.ns) {
+		cudaFree(w->code); cudaFree(w->drift);
+		w->code = nullptr; w->drift = nullptr;
+		size_t n = (size_t)g.nf * g.ns;
+		FG_CUDA(cudaMalloc(&w->code, n));
+		FG_CUDA(cudaMalloc(&w->drift, n * 4));
+		w->nf = g.nf; w->ns = g.ns; w->iters = 0;
+		if (!w->counter) FG_CUDA(cudaMalloc(&w->counter, 4));
+		int dev = 0;
+		FG_CUDA(cudaGetDevice(&dev));
+		FG_CUDA(cudaDeviceGetAttribute(&w->sms, cudaDevAttrMultiProcessorCount, dev));
+	}
+	if (w->iters != iters) {
+		int nq = (iters + kMaxChunk - 1) / kMaxChunk;
+		int kc = (iters + nq - 1) / nq;
+		int ni = (g.nf - 2 + kc - 1 + kTile - 1) / kTile, nj = (g.ns - 2 + kc - 1 + kTile - 1) / kTile;
+		std::vector<int4> tiles;
+		tiles.reserve((size_t)ni * nj * nq);
+		int wmax = (ni - 1) + (nj - 1) + 3 * (nq - 1);
+		for (int wv = 0; wv <= wmax; wv++)
+			for (int q = 0; q < nq; q++) {
+				int d = wv - 3 * q;
+				if (d < 0) break;
+				int kq = std::min(kc, iters - q * kc);
+				for (int I = std::max(0, d - (nj - 1)); I <= std::min(ni - 1, d); I++) tiles.push_back(make_int4(I, d - I, q, kq));
+			}
+		cudaFree(w->tiles); cudaFree(w->flags);
+		w->tiles = nullptr; w->flags = nullptr;
+		FG_CUDA(cudaMalloc(&w->tiles, tiles.size() * sizeof(int4)));
+		FG_CUDA(cudaMalloc(&w->flags, (size_t)ni * nj * nq * 4));
+		FG_CUDA(cudaMemcpyAsync(w->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+		FG_CUDA(cudaMemsetAsync(w->flags, 0, (size_t)ni * nj * nq * 4, st));
+		FG_CUDA(cudaStreamSynchronize(st));  // tiles is a host temporary
+		w->iters = iters; w->kc = kc; w->ni = ni; w->nj = nj; w->nq = nq; w->n_tiles = (int)tiles.size();
+		w->epoch = 0;
+	}
+	return FLIPGPU_OK;
+}
+
+// s must be 0/1-valued (checked by the caller); arbitrary float s takes the plain wavefront kernel of sor.cu
+int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
+                    LaunchCounter* lc) {
+	if (iters <= 0 || g.nf < 3 || g.ns < 3) return FLIPGPU_OK;
+	if (!*wsp) *wsp = new SorWorkspace;
+	SorWorkspace* w = *wsp;
+	FG_TRY(plan(w, g, iters, st));
+	bool use_drift = drift && g.density && g.rest;
+	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr);
+	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
+	w->epoch++;
+	TiledArgs A;
+	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
+	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
+	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega;
+	dim3 block(kTile, w->kc);
+	int per_sm = 0;
+	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true> : (const void*)sor_gs_tiled_kernel<true, false>)
+	                          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true> : (const void*)sor_gs_tiled_kernel<false, false>);
+	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * w->kc, 0));
+	int blocks = std::min(w->n_tiles, std::max(1, per_sm) * w->sms);
+	void* args[] = {&A};
+	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, 0, st));
+	if (lc) lc->n += 2;
+	return FLIPGPU_OK;
+}
+
+}  // namespace fg

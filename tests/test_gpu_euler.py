@@ -32,13 +32,14 @@ def test_scene_builder_matches_ui_shell():
         assert_bit_equal(sim.readback(n), getattr(o, n), f"scene {n}")
 
 
-def test_projection_wavefront_bit_identical(tunnel):
+@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL])
+def test_projection_wavefront_bit_identical(tunnel, order):
     o = co.make_euler_scene(96, 72, oracle_kind="port")
     for n in ("u", "v", "m", "solid"):
         getattr(o, n)[:] = getattr(tunnel, n)
     sim = gpu_from(o)
     o.solve(40, DT)
-    sim.solveIncompressibility(40, DT, solver_order=sg.LEX_WAVEFRONT)
+    sim.solveIncompressibility(40, DT, solver_order=order)
     for n in ("u", "v", "pressure"):
         assert_bit_equal(sim.readback(n), getattr(o, n), f"E1 {n}")
 
