@@ -176,7 +176,7 @@ class FlipFluidGPU:
 
     def simulate(self, dt, gravity, flip_ratio, num_pressure_iters, num_particle_iters, over_relaxation,
                  compensate_drift, separate_particles, obstacle_x, obstacle_y, obstacle_vel_x, obstacle_vel_y,
-                 obstacle_radius, n_steps=1, solver_order=RED_BLACK, update_colors=True):
+                 obstacle_radius, n_steps=1, solver_order=LEX_WAVEFRONT, update_colors=True):
         """FlipFluid::simulate, flip_fluid.h:560-565 (the first 13 arguments are the reference's)."""
         sp = _FlipStepParams(dt, gravity, flip_ratio, num_pressure_iters, num_particle_iters, over_relaxation,
                              int(compensate_drift), int(separate_particles), obstacle_x, obstacle_y,
@@ -203,7 +203,7 @@ class FlipFluidGPU:
     def transferVelocitiesToGrid(self):  # transferVelocities(true) + updateParticleDensity
         _check(self._lib.flip_phase_p2g(self._h), "flip_phase_p2g")
 
-    def solveIncompressibility(self, num_iters, dt, over_relaxation, compensate_drift=True, solver_order=RED_BLACK):
+    def solveIncompressibility(self, num_iters, dt, over_relaxation, compensate_drift=True, solver_order=LEX_WAVEFRONT):
         _check(self._lib.flip_phase_solve(self._h, int(num_iters), C.c_float(dt), C.c_float(over_relaxation),
                                           int(compensate_drift), int(solver_order)), "flip_phase_solve")
 
@@ -303,7 +303,7 @@ class FluidGPU:
         fid, _ = EULER_FIELDS[name]
         _check(self._lib.euler_upload(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"euler_upload({name})")
 
-    def solveIncompressibility(self, num_iter, dt, solver_order=RED_BLACK):
+    def solveIncompressibility(self, num_iter, dt, solver_order=LEX_WAVEFRONT):
         _check(self._lib.euler_project(self._h, int(num_iter), C.c_float(dt), int(solver_order)), "euler_project")
 
     def extrapolate(self):
@@ -315,7 +315,7 @@ class FluidGPU:
     def advectSmoke(self, dt):
         _check(self._lib.euler_advect_smoke(self._h, C.c_float(dt)), "euler_advect_smoke")
 
-    def step(self, num_iter, dt, n_steps=1, solver_order=RED_BLACK):
+    def step(self, num_iter, dt, n_steps=1, solver_order=LEX_WAVEFRONT):
         """the caller sequence of eulerian_fluid/src/fluid_ui.h:107-111"""
         _check(self._lib.euler_step(self._h, int(num_iter), C.c_float(dt), int(solver_order), int(n_steps)), "euler_step")
 
