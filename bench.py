@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 METRIC = "flip_particle_steps_per_s"
 UNIT = "particle-steps/s"
 BENCH_N = 4096
+TRAFFIC_NCU = None   # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from profiles/ (ncu --set full)
 WORKLOAD = "flip_fluid synthetic dam-break 4096^2 grid, 64264080 particles, 50 SOR iters, 2 separation sweeps (BASELINE configs[2])"
 
 
@@ -152,6 +153,24 @@ def product_arm(args, rank, world, local_rank):
     P, nx, ny = sim.num_particles, sim.f_num_x, sim.f_num_y
     iters = kw["num_pressure_iters"]
     stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+    # initial state kept in pinned host memory: the scene is re-seeded (untimed) every SEG timed steps, because the
+    # SURVEY dam-break rule (dt=(1/60)(100/N), 50 sweeps) diverges IN THE REFERENCE ITSELF after ~15 steps at N>=2048
+    # (profiles/r1_stability.md); every timed step therefore runs on a state the reference also produces.
+    SEG = 12
+    h_pos0 = torch.from_numpy(sim.readback("particle_pos")).pin_memory()
+    h_zero_p = torch.zeros(2 * P, dtype=torch.float32).pin_memory()
+    h_zero_c = torch.zeros(nx * ny, dtype=torch.float32).pin_memory()
+    h_s = torch.from_numpy(sim.readback("s")).pin_memory()
+
+    def reseed():
+        sim.num_particles = P
+        sim.upload_from("particle_pos", h_pos0.data_ptr(), 2 * P)
+        sim.upload_from("particle_vel", h_zero_p.data_ptr(), 2 * P)
+        for name in ("u", "v", "prev_u", "prev_v", "p", "particle_density"):
+            sim.upload_from(name, h_zero_c.data_ptr(), nx * ny)
+        sim.upload_from("s", h_s.data_ptr(), nx * ny)
+        sim.particle_rest_density = 0.0
+        sim.simulate(**kw, n_steps=args.warmup, update_colors=False)   # untimed warm-up after every (re)seed
 
     def barrier():
         sim.synchronize()
@@ -167,14 +186,24 @@ def product_arm(args, rank, world, local_rank):
     launches0 = sim.launch_count
     clocks = ClockSampler(local_rank)
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    sim.simulate(**kw, n_steps=args.steps, update_colors=False)
-    e1.record(stream)
-    barrier()
+    ms, done, launches = 0.0, 0, 0
+    while done < args.steps:
+        n = min(SEG, args.steps - done)
+        if done > 0:
+            sim.enable_timings(False)
+            reseed()
+            barrier()
+            sim.enable_timings(True)
+            launches0 = sim.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.simulate(**kw, n_steps=n, update_colors=False)
+        e1.record(stream)
+        barrier()
+        ms += e0.elapsed_time(e1)
+        launches += sim.launch_count - launches0
+        done += n
     clk = clocks.stop()
-    ms = e0.elapsed_time(e1)
-    launches = sim.launch_count - launches0
     phases = sim.timings()
     sim.enable_timings(False)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -186,8 +215,8 @@ def product_arm(args, rank, world, local_rank):
     #      (the s field that FluidUI::setObstacle rewrites every frame, main.cpp:106-122) and the array the caller
     #      reads every frame comes back D2H (particle_pos, main.cpp:173-176), in caller particle order.
     e2e_steps = max(2, min(args.steps, 5))
-    h_s = torch.from_numpy(sim.readback("s")).pin_memory()
     h_pos = torch.empty(2 * P, dtype=torch.float32).pin_memory()
+    reseed()
     barrier()
     t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -216,11 +245,11 @@ def product_arm(args, rank, world, local_rank):
     s_per_step = ms_max * 1e-3 / args.steps
     interior = (nx - 2) * (ny - 2)
     C = nx * ny
-    # roofline of the dominant kernel = one red-black colour pass of the SOR solve
+    # roofline of the dominant kernel = the blocked-wavefront SOR solve (one persistent launch per step)
     solve_ms_per_step = phases["solve"] / args.steps
-    n_solver_launches = 2 * iters
+    n_solver_launches = 1
     launch_s = solve_ms_per_step * 1e-3 / n_solver_launches
-    alg_bytes_per_launch = 36.0 * interior / 2.0          # 36 B per cell-update x half the interior per colour pass
+    alg_bytes_per_launch = 36.0 * interior * iters           # 36 B per cell-update x interior x iters per launch
     achieved = alg_bytes_per_launch / launch_s / 1e9
     step_bytes = 140.0 * P + (96.0 + 36.0 * iters) * C      # SURVEY 8d whole-step formula
     line = {
@@ -229,8 +258,9 @@ def product_arm(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD if N == BENCH_N else f"flip_fluid synthetic dam-break {N}^2 (non-default --grid)",
                    "grid": [nx, ny], "particles_per_gpu": P, "pressure_iters": iters, "separation_sweeps": 2,
-                   "solver_order": "red_black", "colours": "off (render state, SURVEY 8d)",
+                   "solver_order": "lexicographic (blocked wavefront, bit-identical to the reference order)", "colours": "off (render state, SURVEY 8d)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent tanks, one per GPU (no halo exchange yet)",
+                   "reseed": f"state re-seeded (untimed, +{args.warmup} warm-up steps) every {SEG} timed steps: the dam-break rule diverges in the reference itself after ~15 steps (profiles/r1_stability.md)",
                    "l2": "working set ~4.7 GB per step >> 126 MB L2 (no flush needed)",
                    "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
@@ -239,7 +269,7 @@ def product_arm(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(h_pos.numel() * 4), "steps": e2e_steps,
                 "what": "flip_upload(s) + flip_step + flip_readback(particle_pos, caller order), pinned host buffers"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "sor_rb_pass_kernel (one colour pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "sor_gs_tiled_kernel (+ sor_prep_kernel; whole 50-iteration solve in one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches},
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / s_per_step / 1e9, "unit": "GB/s",
@@ -264,7 +294,7 @@ def product_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="flipgpu", choices=["flipgpu", "reference"])
     ap.add_argument("--grid", type=int, default=BENCH_N, help="cells per side of the synthetic dam-break (default: the BASELINE config)")

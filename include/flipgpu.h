@@ -131,6 +131,8 @@ int flip_reset_timings(FlipSim* sim);
 int flip_enable_timings(FlipSim* sim, int on);
 /* kernels launched by this handle since creation (all hand-written sm_100a kernels of this library) */
 int flip_get_launch_count(FlipSim* sim, long long* launches);
+/* diagnostic (FLIPGPU_SOR_PROFILE=1): SM cycles per phase of the blocked solver: wait, load, compute, write-back, tiles, n_tiles, Kc, chunks */
+int flip_debug_solver_profile(FlipSim* sim, unsigned long long* out8);
 
 /* scene helper = the particle lattice + tank walls of flip_fluid/src/main.cpp:47-77 written into host
  * buffers (pos: 2*max floats, s: nx*ny floats); returns the particle count through *num_particles.

@@ -69,6 +69,7 @@ struct SorGrid {
 
 struct SorWorkspace;  // plan + per-cell constants of the blocked-wavefront solver (sor_tiled.cu)
 void sor_workspace_free(SorWorkspace* w);
+int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]);
 int sor_solve_tiled(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
                     LaunchCounter* lc);
 // order: FlipSolverOrder.  s_binary: every s is 0 or 1 (required by the blocked kernel's 1-byte cell code;

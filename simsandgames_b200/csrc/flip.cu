@@ -1175,6 +1175,12 @@ int flip_get_timings(FlipSim* f, float* ms, int count) {
 	for (int i = 0; i < count && i < FLIP_PH_COUNT; i++) ms[i] = f->ph_ms[i];
 	return FLIPGPU_OK;
 }
+int flip_debug_solver_profile(FlipSim* f, unsigned long long* out8) {
+	FG_CHECK(f && out8, FLIPGPU_EINVAL, "null argument");
+	DeviceGuard guard(f->device);
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	return sor_workspace_profile(f->ws, out8);
+}
 int flip_get_launch_count(FlipSim* f, long long* launches) {
 	FG_CHECK(f && launches, FLIPGPU_EINVAL, "null argument");
 	*launches = f->lc.n;

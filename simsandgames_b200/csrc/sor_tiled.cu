@@ -20,6 +20,7 @@
 //     wave order I+J+3q from an atomic counter and wait on completion flags of earlier tiles only.
 // HBM traffic per solve is ~(1+2Kc/T) grid sweeps per chunk of Kc iterations instead of Kc sweeps, with
 // no redundant computation (skewing, not halo recompute).  Compiled with -fmad=false.
+#include <cstdlib>
 #include <vector>
 #include "common.cuh"
 
@@ -42,6 +43,7 @@ struct TiledArgs {
 	int* counter;
 	int epoch;
 	float cp, omega;
+	unsigned long long* prof;  // [0] wait [1] load [2] compute [3] write-back cycles (thread 0 of every CTA), [4] tiles
 };
 
 __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 		if (ti >= A.n_tiles) return;
 		const int4 tl = A.tiles[ti];
 		const int I = tl.x, J = tl.y, q = tl.z, kq = tl.w;
+		long long c0 = clock64();
 		if (tid == 0) {
 			if (I > 0) wait_flag(A.flags + (q * A.nj + J) * A.ni + I - 1, A.epoch);
 			if (J > 0) wait_flag(A.flags + (q * A.nj + J - 1) * A.ni + I, A.epoch);
@@ -73,6 +76,7 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 			__threadfence();
 		}
 		__syncthreads();
+		long long c1 = clock64();
 		const int F0 = 1 + I * kTile, S0 = 1 + J * kTile;
 		const int FB = F0 - A.kc + 1, SB = S0 - A.kc + 1;  // box origin (cells FB..FB+kBoxW-1)
 		// ---- stage the box (L2-coherent loads: the producers are other CTAs of this launch)
@@ -91,15 +95,17 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 			if (DRIFT) s_dr[e] = dr;
 		}
 		__syncthreads();
-		// ---- 2T-1 local diagonals; on each, every iteration of the chunk in parallel
+		long long c2 = clock64();
+		// ---- 2T-1 local diagonals; on each, every iteration of the chunk in parallel.
+		// Lane a owns local column a: it is busy on steps t in [a, a+T-1] and walks down its box column by one
+		// row per step.  Cells outside the grid interior carry code 0 (sor_prep_kernel / the box fill), so no
+		// bounds tests are needed here.
 		const int a = threadIdx.x;
 		for (int t = 0; t < 2 * kTile - 1; t++) {
-			int b = t - a;
-			if (b >= 0 && b < kTile) {
+			if (t >= a && t < a + kTile) {
 				for (int k = threadIdx.y; k < kq; k += blockDim.y) {
-					int F = F0 - k + a, S = S0 - k + b;
-					if (F < 1 || F > nf - 2 || S < 1 || S > ns - 2) continue;
-					int e = (F - FB) + kBoxW * (S - SB);
+					// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
+					int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
 					unsigned cd = s_code[e];
 					if (!(cd & 1u)) continue;
 					float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
@@ -122,6 +128,7 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 			}
 			__syncthreads();
 		}
+		long long c3 = clock64();
 		// ---- write back exactly what this tile owns: cells it updated, plus their high-side faces
 		for (int e = tid; e < kBoxW * kBoxW; e += nthreads) {
 			int lf = e % kBoxW, ls = e / kBoxW;
@@ -143,7 +150,15 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 		}
 		__threadfence();
 		__syncthreads();
-		if (tid == 0) *((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
+		if (tid == 0) {
+			*((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
+			if (A.prof) {
+				long long c4 = clock64();
+				atomicAdd(A.prof + 0, (unsigned long long)(c1 - c0)); atomicAdd(A.prof + 1, (unsigned long long)(c2 - c1));
+				atomicAdd(A.prof + 2, (unsigned long long)(c3 - c2)); atomicAdd(A.prof + 3, (unsigned long long)(c4 - c3));
+				atomicAdd(A.prof + 4, 1ull);
+			}
+		}
 	}
 }
 
@@ -177,12 +192,22 @@ struct SorWorkspace {
 	int4* tiles = nullptr;
 	int* flags = nullptr;
 	int* counter = nullptr;
+	unsigned long long* prof = nullptr;
 	int sms = 0;
 };
 
+// diagnostic: cycles spent per tile phase (enabled by FLIPGPU_SOR_PROFILE=1 in the environment at plan time)
+int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]) {
+	for (int i = 0; i < 8; i++) out[i] = 0;
+	if (!w || !w->prof) return FLIPGPU_ESTATE;
+	FG_CUDA(cudaMemcpy(out, w->prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	out[5] = (unsigned long long)w->n_tiles; out[6] = (unsigned long long)w->kc; out[7] = (unsigned long long)w->nq;
+	return FLIPGPU_OK;
+}
+
 void sor_workspace_free(SorWorkspace* w) {
 	if (!w) return;
-	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter);
+	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter); cudaFree(w->prof);
 	delete w;
 }
 
@@ -195,6 +220,10 @@ static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
 		FG_CUDA(cudaMalloc(&w->drift, n * 4));
 		w->nf = g.nf; w->ns = g.ns; w->iters = 0;
 		if (!w->counter) FG_CUDA(cudaMalloc(&w->counter, 4));
+		if (!w->prof && getenv("FLIPGPU_SOR_PROFILE")) {
+			FG_CUDA(cudaMalloc(&w->prof, 8 * sizeof(unsigned long long)));
+			FG_CUDA(cudaMemset(w->prof, 0, 8 * sizeof(unsigned long long)));
+		}
 		int dev = 0;
 		FG_CUDA(cudaGetDevice(&dev));
 		FG_CUDA(cudaDeviceGetAttribute(&w->sms, cudaDevAttrMultiProcessorCount, dev));
@@ -240,7 +269,7 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	TiledArgs A;
 	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
-	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega;
+	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega; A.prof = w->prof;
 	dim3 block(kTile, w->kc);
 	int per_sm = 0;
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true> : (const void*)sor_gs_tiled_kernel<true, false>)
