@@ -74,7 +74,8 @@ typedef enum {
 	FLIP_SOLVER_RED_BLACK = 0,     /* performance order (north_star); bounded against the reference order */
 	FLIP_SOLVER_LEX_WAVEFRONT = 1, /* the reference's lexicographic loop order (flip_fluid.h:458-494) as a blocked
 	                                  anti-diagonal wavefront in shared memory: bit-identical u,v,p */
-	FLIP_SOLVER_LEX_DIAGONAL = 2   /* same order, unblocked one-diagonal-per-grid-sync kernel (cross-check / non-binary s) */
+	FLIP_SOLVER_LEX_DIAGONAL = 2,  /* same order, unblocked one-diagonal-per-grid-sync kernel (cross-check / non-binary s) */
+	FLIP_SOLVER_LEX_STRIPS = 3     /* same order, streaming skewed tile columns instead of square tiles (experimental, slower in r1) */
 } FlipSolverOrder;
 
 /* the 13 arguments of FlipFluid::simulate (flip_fluid.h:560-565) + two switches */

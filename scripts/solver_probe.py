@@ -13,5 +13,6 @@ out = (C.c_ulonglong * 8)(); sim._lib.flip_debug_solver_profile(sim._h, out)
 d = [out[i] - out0[i] for i in range(5)]
 tiles = d[4]
 print("solve ms/step", sim.timings()["solve"] / K, "tiles/solve", out[5], "Kc", out[6], "chunks", out[7])
-for name, v in zip(("wait", "load", "compute", "writeback"), d[:4]):
-    print(f"  {name:10s} {v / tiles:10.0f} cycles/tile  ({v / tiles / 1.9e3:.2f} us @1.9GHz)")
+for name, v in zip(("dep wait", "compute", "other", "-"), d[:4]):
+    print(f"  {name:10s} {v / tiles:12.0f} cycles/strip  ({v / tiles / 1.9e3:.1f} us @1.9GHz)")
+print("  strips per solve", tiles / K)

@@ -18,6 +18,7 @@ _LIB = None
 RED_BLACK = 0
 LEX_WAVEFRONT = 1
 LEX_DIAGONAL = 2
+LEX_STRIPS = 3
 
 FLIP_FIELDS = {  # name -> (enum value, numpy dtype)   order == FlipField in flipgpu.h
     "u": (0, np.float32), "v": (1, np.float32), "du": (2, np.float32), "dv": (3, np.float32),

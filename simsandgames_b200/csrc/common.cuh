@@ -72,6 +72,8 @@ void sor_workspace_free(SorWorkspace* w);
 int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]);
 int sor_solve_tiled(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
                     LaunchCounter* lc);
+int sor_solve_strips(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
+                     LaunchCounter* lc);
 // order: FlipSolverOrder.  s_binary: every s is 0 or 1 (required by the blocked kernel's 1-byte cell code;
 // otherwise LEX_WAVEFRONT falls back to the unblocked diagonal kernel, same results).
 int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,

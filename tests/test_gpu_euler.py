@@ -32,7 +32,7 @@ def test_scene_builder_matches_ui_shell():
         assert_bit_equal(sim.readback(n), getattr(o, n), f"scene {n}")
 
 
-@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL])
+@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL, sg.LEX_STRIPS])
 def test_projection_wavefront_bit_identical(tunnel, order):
     o = co.make_euler_scene(96, 72, oracle_kind="port")
     for n in ("u", "v", "m", "solid"):
