@@ -38,6 +38,8 @@ struct TiledArgs {
 	const unsigned char* code;  // bit0 active, bit1..4 = s != 0 at fast-, fast+, slow-, slow+ neighbour
 	const float* drift;         // max(0, density-rest) when drift compensation applies, else nullptr
 	const int4* tiles;          // (I, J, q, kq) in wave order
+	const unsigned char* act;   // act[J0*na + I0] != 0: the unskewed TxT square (I0,J0) holds a cell the solver updates
+	int na, nb;
 	int n_tiles, ni, nj, kc;
 	int* flags;                 // flags[(q*nj+J)*ni+I] == epoch  <=> tile complete
 	int* counter;
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 	const int nthreads = kTile * blockDim.y;
 	const int nf = A.nf, ns = A.ns;
 	for (;;) {
+		__syncthreads();
 		if (tid == 0) s_tile = atomicAdd(A.counter, 1);
 		__syncthreads();
 		const int ti = s_tile;
@@ -77,6 +80,16 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 		}
 		__syncthreads();
 		long long c1 = clock64();
+		{	// the skewed tile lies inside the four unskewed squares (I-1..I, J-1..J): if none of them holds an active
+			// cell (all air / solid) the tile changes nothing -- publish it at once (dam-break: about half the tiles)
+			bool any = false;
+			for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
+				for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any |= A.act[jj * A.na + ii] != 0;
+			if (!any) {
+				if (tid == 0) *((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
+				continue;
+			}
+		}
 		const int F0 = 1 + I * kTile, S0 = 1 + J * kTile;
 		const int FB = F0 - A.kc + 1, SB = S0 - A.kc + 1;  // box origin (cells FB..FB+kBoxW-1)
 		// ---- stage the box (L2-coherent loads: the producers are other CTAs of this launch)
@@ -108,22 +121,23 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 					int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
 					unsigned cd = s_code[e];
 					if (!(cd & 1u)) continue;
-					float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
-					float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
-					float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
 					float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[e + kBoxW];
 					float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
-					if (DRIFT) {
-						float compression = s_dr[e];
-						if (compression > 0.f) div -= compression;
+					if (DRIFT) div -= s_dr[e];   // the stored term is max(0, density-rest): subtracting 0 is exact
+					if (cd == 31u) {             // all four neighbours open: s_sum = 4 and x/4 == x*0.25 exactly
+						float pv = (-div * 0.25f) * A.omega;
+						s_p[e] += A.cp * pv;
+						s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[e + kBoxW] = vsp + pv;
+					} else {
+						float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
+						float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
+						float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+						float pv = -div / ssum;
+						pv *= A.omega;
+						s_p[e] += A.cp * pv;
+						s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
+						s_vs[e] = vsc - ssm * pv; s_vs[e + kBoxW] = vsp + ssp * pv;
 					}
-					float pv = -div / ssum;
-					pv *= A.omega;
-					s_p[e] += A.cp * pv;
-					s_vf[e] = vfc - sfm * pv;
-					s_vf[e + 1] = vfp + sfp * pv;
-					s_vs[e] = vsc - ssm * pv;
-					s_vs[e + kBoxW] = vsp + ssp * pv;
 				}
 			}
 			__syncthreads();
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 
 // per-solve constants of every cell: the neighbour-openness code and the drift term
 __global__ void __launch_bounds__(256) sor_prep_kernel(SorGrid g, bool drift, unsigned char* __restrict__ code,
-                                                       float* __restrict__ drift_out) {
+                                                       float* __restrict__ drift_out, unsigned char* __restrict__ act, int na) {
 	float rest = (drift && g.rest) ? *g.rest : 0.f;
 	size_t n = (size_t)g.nf * g.ns;
 	for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(256) sor_prep_kernel(SorGrid g, bool drift, un
 		}
 		code[c] = (unsigned char)cd;
 		if (drift_out) drift_out[c] = dr;
+		if (cd && act) act[((b - 1) / kTile) * na + (a - 1) / kTile] = 1;  // racing writers store the same value
 	}
 }
 
@@ -192,6 +207,8 @@ struct SorWorkspace {
 	int4* tiles = nullptr;
 	int* flags = nullptr;
 	int* counter = nullptr;
+	unsigned char* act = nullptr;  // activity of the unskewed TxT squares
+	int na = 0, nb = 0;
 	unsigned long long* prof = nullptr;
 	int2* strips = nullptr;   // (I, q) in wave order I + 2q (streaming-strip kernel)
 	int* progress = nullptr;  // per strip: rows S < progress are final in global memory
@@ -210,7 +227,7 @@ int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]) {
 
 void sor_workspace_free(SorWorkspace* w) {
 	if (!w) return;
-	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter); cudaFree(w->prof); cudaFree(w->strips); cudaFree(w->progress);
+	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter); cudaFree(w->prof); cudaFree(w->strips); cudaFree(w->progress); cudaFree(w->act);
 	delete w;
 }
 
@@ -221,6 +238,9 @@ static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
 		size_t n = (size_t)g.nf * g.ns;
 		FG_CUDA(cudaMalloc(&w->code, n));
 		FG_CUDA(cudaMalloc(&w->drift, n * 4));
+		cudaFree(w->act);
+		w->na = (g.nf - 2 + kTile - 1) / kTile; w->nb = (g.ns - 2 + kTile - 1) / kTile;
+		FG_CUDA(cudaMalloc(&w->act, (size_t)w->na * w->nb));
 		w->nf = g.nf; w->ns = g.ns; w->iters = 0;
 		if (!w->counter) FG_CUDA(cudaMalloc(&w->counter, 4));
 		if (!w->prof && getenv("FLIPGPU_SOR_PROFILE")) {
@@ -282,13 +302,15 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	SorWorkspace* w = *wsp;
 	FG_TRY(plan(w, g, iters, st));
 	bool use_drift = drift && g.density && g.rest;
-	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr);
+	FG_CUDA(cudaMemsetAsync(w->act, 0, (size_t)w->na * w->nb, st));
+	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, w->act, w->na);
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
 	w->epoch++;
 	TiledArgs A;
 	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
 	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega; A.prof = w->prof;
+	A.act = w->act; A.na = w->na; A.nb = w->nb;
 	dim3 block(kTile, w->kc);
 	int per_sm = 0;
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true> : (const void*)sor_gs_tiled_kernel<true, false>)
@@ -517,7 +539,7 @@ int sor_solve_strips(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, 
 	SorWorkspace* w = *wsp;
 	FG_TRY(plan(w, g, iters, st));
 	bool use_drift = drift && g.density && g.rest;
-	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr);
+	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, nullptr, 0);
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
 	FG_CUDA(cudaMemsetAsync(w->progress, 0, (size_t)w->ni * w->nq * 4, st));
 	StripArgs A;
