@@ -197,6 +197,22 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int* __restri
 	}
 }
 
+
+// Sort a short run held in registers with an odd-even transposition network (fully unrolled, compile-time
+// indices).  Cell segments hold a handful of particles, so this replaces the read-modify-write insertion sort
+// on global memory for every run of up to N elements; longer runs fall back to the in-place insertion sort.
+template <int N, typename T>
+__device__ __forceinline__ void sort_network_ascending(T (&v)[N]) {
+#pragma unroll
+	for (int r = 0; r < N; r++) {
+#pragma unroll
+		for (int i = (r & 1); i + 1 < N; i += 2) {
+			T lo = v[i] < v[i + 1] ? v[i] : v[i + 1], hi = v[i] < v[i + 1] ? v[i + 1] : v[i];
+			v[i] = lo; v[i + 1] = hi;
+		}
+	}
+}
+
 // ------------------------------------------------------------------ F2: fill (flip_fluid.h:189-198)
 // Slots are claimed with atomicSub (any order) ...
 __global__ void __launch_bounds__(kThreads) k_fill(int np, const int* __restrict__ keys, const int* __restrict__ orig,
@@ -216,7 +232,35 @@ __global__ void __launch_bounds__(kThreads) k_fixup_cells(int n_cells, const int
 		int n = count[c];
 		if (n < 2) continue;
 		int b = first[c];
-		for (int i = 1; i < n; i++) {  // insertion sort, descending id; segments hold a handful of particles
+		// (id, src) packed into one 64-bit key, negated: ascending order of the key == descending id (ids are unique)
+		if (n == 2) {
+			int i0 = ids[b], i1 = ids[b + 1];
+			if (i0 < i1) { int s0 = src[b], s1 = src[b + 1]; ids[b] = i1; ids[b + 1] = i0; src[b] = s1; src[b + 1] = s0; }
+			continue;
+		}
+		if (n <= 4) {
+			long long v[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+				v[i] = i < n ? -(((long long)ids[b + i] << 32) | (unsigned)src[b + i]) : 0x7fffffffffffffffll;
+			sort_network_ascending<4>(v);
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+				if (i < n) { long long w = -v[i]; ids[b + i] = (int)(w >> 32); src[b + i] = (int)(w & 0xffffffffll); }
+			continue;
+		}
+		if (n <= 8) {
+			long long v[8];
+#pragma unroll
+			for (int i = 0; i < 8; i++)
+				v[i] = i < n ? -(((long long)ids[b + i] << 32) | (unsigned)src[b + i]) : 0x7fffffffffffffffll;
+			sort_network_ascending<8>(v);
+#pragma unroll
+			for (int i = 0; i < 8; i++)
+				if (i < n) { long long w = -v[i]; ids[b + i] = (int)(w >> 32); src[b + i] = (int)(w & 0xffffffffll); }
+			continue;
+		}
+		for (int i = 1; i < n; i++) {  // insertion sort, descending id (crowded cells only)
 			int id = ids[b + i], sv = src[b + i];
 			int j = i - 1;
 			while (j >= 0 && ids[b + j] < id) {
@@ -288,27 +332,50 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 		int pxi = (int)(p.x * g.p_inv), pyi = (int)(p.y * g.p_inv);
 		int x0 = max(pxi - 1, 0), y0 = max(pyi - 1, 0);
 		int x1 = min(pxi + 1, g.pnx - 1), y1 = min(pyi + 1, g.pny - 1);
-		if (x0 <= x1)
-			for (int yi = y0; yi <= y1; yi++) {
-				int a = first[x0 + g.pnx * yi], b = first[x1 + g.pnx * yi + 1];
-				for (int j = a; j < b; j++) {
-					if (j == t) continue;
-					float2 q = pos_in[j];
-					float dx = q.x - p.x, dy = q.y - p.y;
-					float d2 = dx * dx + dy * dy;
-					if (d2 > min_dist_sq || d2 == 0.f) continue;
-					float d = sqrtf(d2);
-					float sc = .5f * (min_dist - d) / d;
-					ax -= dx * sc;
-					ay -= dy * sc;
-					if (COLORS) {  // colour diffusion toward the pair mean, flip_fluid.h:239-245
-						float q0 = col_in[3 * (size_t)j], q1 = col_in[3 * (size_t)j + 1], q2 = col_in[3 * (size_t)j + 2];
-						c0 += .001f * ((c0 + q0) / 2.f - c0);
-						c1 += .001f * ((c1 + q1) / 2.f - c1);
-						c2 += .001f * ((c2 + q2) / 2.f - c2);
-					}
+		// the (up to) three window rows are three contiguous slot ranges; candidates are numbered through them
+		int ra[3], rn[3];
+#pragma unroll
+		for (int r = 0; r < 3; r++) {
+			int yi = y0 + r;
+			bool on = x0 <= x1 && yi <= y1;
+			ra[r] = on ? first[x0 + g.pnx * yi] : 0;
+			rn[r] = on ? first[x1 + g.pnx * yi + 1] - ra[r] : 0;
+		}
+		const int n_all = rn[0] + rn[1] + rn[2];
+		// Two passes per chunk of 32 candidates keep the warp converged: pass 1 is the cheap distance test and leaves
+		// a bit mask of overlapping partners; pass 2 runs the sqrt/divide push only for the set bits, in candidate
+		// order (the order of the adds is part of the schedule: oracle orcflip_separate_jacobi).
+		for (int base = 0; base < n_all; base += 32) {
+			const int n = min(32, n_all - base);
+			unsigned hits = 0;
+			for (int i = 0; i < n; i++) {
+				int k = base + i;
+				int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
+				float2 q = pos_in[j];
+				float dx = q.x - p.x, dy = q.y - p.y;
+				float d2 = dx * dx + dy * dy;
+				if (j != t && !(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
+			}
+			while (hits) {
+				int i = __ffs(hits) - 1;
+				hits &= hits - 1;
+				int k = base + i;
+				int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
+				float2 q = pos_in[j];
+				float dx = q.x - p.x, dy = q.y - p.y;
+				float d2 = dx * dx + dy * dy;
+				float d = sqrtf(d2);
+				float sc = .5f * (min_dist - d) / d;
+				ax -= dx * sc;
+				ay -= dy * sc;
+				if (COLORS) {  // colour diffusion toward the pair mean, flip_fluid.h:239-245
+					float q0 = col_in[3 * (size_t)j], q1 = col_in[3 * (size_t)j + 1], q2 = col_in[3 * (size_t)j + 2];
+					c0 += .001f * ((c0 + q0) / 2.f - c0);
+					c1 += .001f * ((c1 + q1) / 2.f - c1);
+					c2 += .001f * ((c2 + q2) / 2.f - c2);
 				}
 			}
+		}
 		pos_out[t] = make_float2(ax, ay);
 		if (COLORS) { col_out[3 * (size_t)t] = c0; col_out[3 * (size_t)t + 1] = c1; col_out[3 * (size_t)t + 2] = c2; }
 	}
@@ -373,6 +440,16 @@ __global__ void __launch_bounds__(kThreads) k_fixup_grid(int n_cells, const int*
 		int n = gcount[c];
 		if (n < 2) continue;
 		int b = gfirst[c];
+		if (n <= 16) {
+			int v[16];
+#pragma unroll
+			for (int i = 0; i < 16; i++) v[i] = i < n ? gidx[b + i] : 0x7fffffff;
+			sort_network_ascending<16>(v);
+#pragma unroll
+			for (int i = 0; i < 16; i++)
+				if (i < n) gidx[b + i] = v[i];
+			continue;
+		}
 		for (int i = 1; i < n; i++) {
 			int v = gidx[b + i], j = i - 1;
 			while (j >= 0 && gidx[b + j] > v) { gidx[b + j + 1] = gidx[b + j]; j--; }
