@@ -168,6 +168,33 @@ int euler_synchronize(EulerSim* sim);
 int euler_get_stream(EulerSim* sim, void** stream);
 int euler_get_launch_count(EulerSim* sim, long long* launches);
 
+/* ------------------------------------------------------------------ multi-GPU: slab-sharded projection
+ * One process per GPU.  The grid of nf x ns cells (nf = fast/contiguous axis) is cut into nranks slabs of rows
+ * along the slow axis; rank r owns rows [j0,j1) = sorshard_slab(ns, r, nranks) plus one halo row on each side.
+ * sorshard_solve runs red-black SOR sweeps (the update of flip_fluid.h:461-491 / fluid.h:110-135) with one
+ * NCCL neighbour exchange of the shared face row per colour pass; results are bit-identical to the single-GPU
+ * FLIP_SOLVER_RED_BLACK solve.  Rank 0 makes the communicator id, the host program broadcasts it (MPI,
+ * torch.distributed, a file ...) and every rank passes it to sorshard_create. */
+typedef struct SorShard SorShard;
+typedef enum {
+	SORSHARD_VEL_FAST = 0, /* velocity along the fast axis at the low face: u for FlipFluid, v for Fluid */
+	SORSHARD_VEL_SLOW,     /* velocity along the slow axis: v for FlipFluid, u for Fluid */
+	SORSHARD_P, SORSHARD_S, SORSHARD_DENSITY, /* float */
+	SORSHARD_CELL_TYPE     /* int, 0 = fluid */
+} SorShardField;
+int flipgpu_nccl_unique_id(void* out128);                     /* 128 bytes (ncclUniqueId) */
+void sorshard_slab(int ns, int rank, int nranks, int* j0, int* j1);
+int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void* unique_id128, int device, SorShard** out);
+int sorshard_destroy(SorShard* h);
+int sorshard_get_rows(SorShard* h, int* j0, int* j1);
+/* rows [j_start, j_start+n_rows) in global numbering, inside [j0-1, j1+1); host holds n_rows*nf elements */
+int sorshard_upload_rows(SorShard* h, int field, const void* host, int j_start, int n_rows);
+int sorshard_readback_rows(SorShard* h, int field, void* host, int j_start, int n_rows);
+int sorshard_solve(SorShard* h, int iters, float cp, float omega, int compensate_drift, float rest_density);
+int sorshard_synchronize(SorShard* h);
+int sorshard_get_stream(SorShard* h, void** stream);
+int sorshard_get_counters(SorShard* h, long long* launches, long long* exchanges);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,3 +359,81 @@ class FluidGPU:
             self.close()
         except Exception:
             pass
+
+
+SHARD_FIELDS = {"vel_fast": (0, np.float32), "vel_slow": (1, np.float32), "p": (2, np.float32), "s": (3, np.float32),
+                "density": (4, np.float32), "cell_type": (5, np.int32)}
+
+
+def nccl_unique_id():
+    """128-byte NCCL communicator id (rank 0 creates it, the caller broadcasts it)."""
+    buf = (C.c_ubyte * 128)()
+    _check(load_library().flipgpu_nccl_unique_id(buf), "flipgpu_nccl_unique_id")
+    return bytes(buf)
+
+
+def slab_rows(ns, rank, nranks):
+    """Rows [j0, j1) of rank `rank` when ns rows are cut into nranks slabs (same rule as the library)."""
+    j0, j1 = C.c_int(), C.c_int()
+    load_library().sorshard_slab(int(ns), int(rank), int(nranks), C.byref(j0), C.byref(j1))
+    return j0.value, j1.value
+
+
+class ShardedProjection:
+    """One rank's slab of the red-black SOR projection; arrays are (rows, nf) numpy views of global rows."""
+
+    def __init__(self, nf, ns, x_fast, rank, nranks, unique_id=None, device=-1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(self._lib.sorshard_create(int(nf), int(ns), int(bool(x_fast)), int(rank), int(nranks), idbuf, int(device), C.byref(self._h)),
+               "sorshard_create")
+        self.nf, self.ns, self.rank, self.nranks = nf, ns, rank, nranks
+        self.j0, self.j1 = slab_rows(ns, rank, nranks)
+        self.w0, self.w1 = max(self.j0 - 1, 0), min(self.j1 + 1, ns)   # window incl. halo rows
+
+    def upload_window(self, name, global_array):
+        """Copy this rank's window rows [j0-1, j1+1) out of a full (ns, nf) host array."""
+        fid, dt = SHARD_FIELDS[name]
+        a = np.ascontiguousarray(np.asarray(global_array).reshape(self.ns, self.nf)[self.w0:self.w1], dtype=dt)
+        _check(self._lib.sorshard_upload_rows(self._h, fid, a.ctypes.data_as(C.c_void_p), self.w0, self.w1 - self.w0), f"sorshard_upload_rows({name})")
+
+    def upload_rows(self, name, rows, j_start):
+        fid, dt = SHARD_FIELDS[name]
+        a = np.ascontiguousarray(rows, dtype=dt).reshape(-1, self.nf)
+        _check(self._lib.sorshard_upload_rows(self._h, fid, a.ctypes.data_as(C.c_void_p), int(j_start), a.shape[0]), f"sorshard_upload_rows({name})")
+
+    def readback_own(self, name):
+        fid, dt = SHARD_FIELDS[name]
+        out = np.empty((self.j1 - self.j0, self.nf), dt)
+        _check(self._lib.sorshard_readback_rows(self._h, fid, out.ctypes.data_as(C.c_void_p), self.j0, self.j1 - self.j0), f"sorshard_readback_rows({name})")
+        return out
+
+    def solve(self, iters, cp, omega, compensate_drift=False, rest_density=0.0):
+        _check(self._lib.sorshard_solve(self._h, int(iters), C.c_float(cp), C.c_float(omega), int(compensate_drift), C.c_float(rest_density)),
+               "sorshard_solve")
+
+    def synchronize(self):
+        _check(self._lib.sorshard_synchronize(self._h), "sorshard_synchronize")
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        _check(self._lib.sorshard_get_stream(self._h, C.byref(s)), "sorshard_get_stream")
+        return s.value or 0
+
+    def counters(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        _check(self._lib.sorshard_get_counters(self._h, C.byref(a), C.byref(b)), "sorshard_get_counters")
+        return a.value, b.value
+
+    def close(self):
+        if self._h:
+            self._lib.sorshard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

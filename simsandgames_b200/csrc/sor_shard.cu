@@ -1,0 +1,260 @@
+// Slab-sharded red-black SOR projection: one process per GPU, one slab of grid rows per rank, one
+// nearest-neighbour NCCL exchange per colour pass (stage "F9, every colour pass").
+//
+// The grid is cut along the SLOW storage axis (rows are contiguous, so a halo row is one contiguous
+// message).  Rank r owns cell rows [j0, j1) and keeps one halo row on each side.  A cell update touches its
+// own faces and the high-side faces of its row (sor.cu), so the only data two ranks share is the face row
+// vel_s[., j1]: during colour pass c the lower rank's cells (a, j1-1) with (a+j1-1)%2==c write it at those
+// columns, the upper rank's cells (a, j1) with (a+j1)%2==c write it at the other columns.  After every pass
+// both ranks swap their copy of that row (ncclSend/ncclRecv in one group over NVLink) and keep, per column,
+// the value written by whoever owned the update -- so every cell update sees exactly the inputs it sees on
+// one GPU and the result is bit-identical to the single-GPU red-black solve (tests/test_gpu_multi.py).
+// The lexicographic wavefront is not sharded: its critical path crosses all slabs.
+#include <nccl.h>
+#include <algorithm>
+#include "common.cuh"
+
+namespace fg {
+
+#define FG_NCCL(call)                                                                          \
+	do {                                                                                       \
+		ncclResult_t r_ = (call);                                                              \
+		if (r_ != ncclSuccess) {                                                               \
+			fg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+			return FLIPGPU_ENCCL;                                                              \
+		}                                                                                      \
+	} while (0)
+
+// one colour of one SOR sweep over local rows [b_lo, b_hi]; `shift` = parity of the global index of local row 0
+template <bool XFAST>
+__global__ void __launch_bounds__(256) sor_rb_rows_kernel(SorGrid g, int colour, int shift, int b_lo, int b_hi, float cp,
+                                                          float omega, bool drift) {
+	int b = b_lo + blockIdx.y * blockDim.y + threadIdx.y;
+	if (b > b_hi) return;
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	int a = 2 * k + ((b + shift + colour) & 1);
+	if (a < 1 || a > g.nf - 2) return;
+	const int nf = g.nf, c = a + nf * b;
+	if (g.cell_type[c] != FLUID_CELL) return;
+	float sfm = g.s[c - 1], sfp = g.s[c + 1], ssm = g.s[c - nf], ssp = g.s[c + nf];
+	float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+	if (ssum == 0.f) return;
+	float vfc = g.vel_f[c], vfp = g.vel_f[c + 1], vsc = g.vel_s[c], vsp = g.vel_s[c + nf];
+	float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
+	float rest = (drift && g.rest) ? *g.rest : 0.f;
+	if (drift && rest > 0.f) {
+		float compression = g.density[c] - rest;
+		if (compression > 0.f) div -= compression;
+	}
+	float pv = -div / ssum;
+	pv *= omega;
+	g.p[c] += cp * pv;
+	g.vel_f[c] = vfc - sfm * pv;
+	g.vel_f[c + 1] = vfp + sfp * pv;
+	g.vel_s[c] = vsc - ssm * pv;
+	g.vel_s[c + nf] = vsp + ssp * pv;
+}
+
+// keep, per column, the neighbour's value where the neighbour's cells wrote the shared face row
+__global__ void merge_face_row_kernel(float* __restrict__ row, const float* __restrict__ recv, int nf, int parity) {
+	int a = blockIdx.x * blockDim.x + threadIdx.x;
+	if (a < nf && (a & 1) == parity) row[a] = recv[a];
+}
+
+}  // namespace fg
+
+using namespace fg;
+
+struct SorShard {
+	int nf = 0, ns = 0, rank = 0, nranks = 1, j0 = 0, j1 = 0, rows = 0, device = 0;
+	bool x_fast = true;
+	float *vel_f = nullptr, *vel_s = nullptr, *p = nullptr, *s = nullptr, *dens = nullptr, *d_rest = nullptr;
+	int* cell_type = nullptr;
+	float *recv_lo = nullptr, *recv_hi = nullptr;
+	ncclComm_t comm = nullptr;
+	cudaStream_t st = nullptr;
+	LaunchCounter lc;
+	long long exchanges = 0;
+};
+
+namespace {
+struct SDeviceGuard {
+	int prev = -1;
+	explicit SDeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); }
+	~SDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+void* shard_field(SorShard* h, int field, size_t* elem) {
+	*elem = 4;
+	switch (field) {
+		case SORSHARD_VEL_FAST: return h->vel_f;
+		case SORSHARD_VEL_SLOW: return h->vel_s;
+		case SORSHARD_P: return h->p;
+		case SORSHARD_S: return h->s;
+		case SORSHARD_DENSITY: return h->dens;
+		case SORSHARD_CELL_TYPE: return h->cell_type;
+	}
+	return nullptr;
+}
+}  // namespace
+
+extern "C" {
+
+int flipgpu_nccl_unique_id(void* out128) {
+	FG_CHECK(out128, FLIPGPU_EINVAL, "null argument");
+	ncclUniqueId id;
+	FG_NCCL(ncclGetUniqueId(&id));
+	static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+	memcpy(out128, &id, sizeof(id));
+	return FLIPGPU_OK;
+}
+
+void sorshard_slab(int ns, int rank, int nranks, int* j0, int* j1) {
+	*j0 = (int)((long long)ns * rank / nranks);
+	*j1 = (int)((long long)ns * (rank + 1) / nranks);
+}
+
+int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void* unique_id128, int device, SorShard** out) {
+	FG_CHECK(out && nf >= 3 && ns >= 3 && nranks >= 1 && rank >= 0 && rank < nranks, FLIPGPU_EINVAL, "sorshard_create: bad argument");
+	FG_CHECK(ns / nranks >= 2, FLIPGPU_EINVAL, "sorshard_create: %d rows over %d ranks leaves slabs thinner than 2 rows", ns, nranks);
+	FG_CHECK(nranks == 1 || unique_id128, FLIPGPU_EINVAL, "sorshard_create: a NCCL unique id is required for %d ranks", nranks);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		fg::set_error("sorshard_create: no CUDA device (this library has no CPU fallback)");
+		return FLIPGPU_ENODEV;
+	}
+	if (device < 0) FG_CUDA(cudaGetDevice(&device));
+	FG_CHECK(device < ndev, FLIPGPU_EINVAL, "sorshard_create: device %d of %d", device, ndev);
+	SorShard* h = new SorShard;
+	h->nf = nf; h->ns = ns; h->rank = rank; h->nranks = nranks; h->device = device; h->x_fast = x_fast != 0;
+	sorshard_slab(ns, rank, nranks, &h->j0, &h->j1);
+	h->rows = h->j1 - h->j0 + 2;  // own rows + one halo row on each side
+	SDeviceGuard guard(device);
+	FG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+	size_t n = (size_t)nf * h->rows;
+	float** fs[] = {&h->vel_f, &h->vel_s, &h->p, &h->s, &h->dens};
+	for (float** f : fs) {
+		FG_CUDA(cudaMalloc(f, n * 4));
+		FG_CUDA(cudaMemsetAsync(*f, 0, n * 4, h->st));
+	}
+	FG_CUDA(cudaMalloc(&h->cell_type, n * 4));
+	FG_CUDA(cudaMemsetAsync(h->cell_type, 0xff, n * 4, h->st));  // -1: not fluid until uploaded
+	FG_CUDA(cudaMalloc(&h->d_rest, 4));
+	FG_CUDA(cudaMemsetAsync(h->d_rest, 0, 4, h->st));
+	FG_CUDA(cudaMalloc(&h->recv_lo, (size_t)nf * 4));
+	FG_CUDA(cudaMalloc(&h->recv_hi, (size_t)nf * 4));
+	FG_CUDA(cudaStreamSynchronize(h->st));
+	if (nranks > 1) {
+		ncclUniqueId id;
+		memcpy(&id, unique_id128, sizeof(id));
+		FG_NCCL(ncclCommInitRank(&h->comm, nranks, id, rank));
+	}
+	*out = h;
+	return FLIPGPU_OK;
+}
+
+int sorshard_destroy(SorShard* h) {
+	if (!h) return FLIPGPU_OK;
+	SDeviceGuard guard(h->device);
+	cudaStreamSynchronize(h->st);
+	if (h->comm) ncclCommDestroy(h->comm);
+	void* ptrs[] = {h->vel_f, h->vel_s, h->p, h->s, h->dens, h->cell_type, h->d_rest, h->recv_lo, h->recv_hi};
+	for (void* p : ptrs) if (p) cudaFree(p);
+	cudaStreamDestroy(h->st);
+	delete h;
+	return FLIPGPU_OK;
+}
+
+int sorshard_get_rows(SorShard* h, int* j0, int* j1) {
+	FG_CHECK(h && j0 && j1, FLIPGPU_EINVAL, "null argument");
+	*j0 = h->j0; *j1 = h->j1;
+	return FLIPGPU_OK;
+}
+
+// rows [j_start, j_start+n_rows) of a field, global row numbering; must lie inside own rows +- the halo row
+static int shard_copy(SorShard* h, int field, void* host, int j_start, int n_rows, bool to_device) {
+	FG_CHECK(h && host, FLIPGPU_EINVAL, "null argument");
+	size_t elem;
+	char* base = (char*)shard_field(h, field, &elem);
+	FG_CHECK(base, FLIPGPU_EINVAL, "sorshard: unknown field %d", field);
+	FG_CHECK(n_rows >= 0 && j_start >= h->j0 - 1 && j_start + n_rows <= h->j1 + 1 && j_start >= 0 && j_start + n_rows <= h->ns,
+	         FLIPGPU_EINVAL, "sorshard: rows [%d,%d) outside this rank's window [%d,%d)", j_start, j_start + n_rows, h->j0 - 1, h->j1 + 1);
+	SDeviceGuard guard(h->device);
+	size_t off = (size_t)(j_start - (h->j0 - 1)) * h->nf * elem, bytes = (size_t)n_rows * h->nf * elem;
+	if (bytes) {
+		if (to_device) FG_CUDA(cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, h->st));
+		else FG_CUDA(cudaMemcpyAsync(host, base + off, bytes, cudaMemcpyDeviceToHost, h->st));
+	}
+	FG_CUDA(cudaStreamSynchronize(h->st));
+	return FLIPGPU_OK;
+}
+int sorshard_upload_rows(SorShard* h, int field, const void* host, int j_start, int n_rows) {
+	return shard_copy(h, field, const_cast<void*>(host), j_start, n_rows, true);
+}
+int sorshard_readback_rows(SorShard* h, int field, void* host, int j_start, int n_rows) {
+	return shard_copy(h, field, host, j_start, n_rows, false);
+}
+
+// iters red-black sweeps (flip_fluid.h:458-494 update, red-black order); p is NOT cleared here
+int sorshard_solve(SorShard* h, int iters, float cp, float omega, int drift, float rest_density) {
+	FG_CHECK(h && iters >= 0, FLIPGPU_EINVAL, "sorshard_solve: bad argument");
+	SDeviceGuard guard(h->device);
+	FG_CUDA(cudaMemcpyAsync(h->d_rest, &rest_density, 4, cudaMemcpyHostToDevice, h->st));
+	SorGrid g;
+	g.nf = h->nf; g.ns = h->rows; g.vel_f = h->vel_f; g.vel_s = h->vel_s; g.p = h->p; g.s = h->s; g.cell_type = h->cell_type;
+	g.density = h->dens; g.rest = h->d_rest; g.x_fast = h->x_fast;
+	// local row l holds global row j0-1+l; interior global rows are 1..ns-2
+	const int b_lo = std::max(h->j0, 1) - (h->j0 - 1), b_hi = std::min(h->j1 - 1, h->ns - 2) - (h->j0 - 1);
+	const int shift = (h->j0 - 1) & 1;
+	const bool use_drift = drift != 0;
+	dim3 block(64, 4);
+	dim3 grid(cdiv((size_t)(h->nf + 1) / 2 + 1, block.x), cdiv((size_t)std::max(b_hi - b_lo + 1, 1), block.y));
+	float* row_hi = h->vel_s + (size_t)(h->rows - 1) * h->nf;  // global row j1  (halo above == the upper rank's first own row)
+	float* row_lo = h->vel_s + (size_t)1 * h->nf;              // global row j0  (own first row; the lower rank's halo above)
+	const bool has_up = h->rank + 1 < h->nranks, has_down = h->rank > 0;
+	for (int it = 0; it < iters; it++)
+		for (int colour = 0; colour < 2; colour++) {
+			if (b_hi >= b_lo) {
+				if (h->x_fast) sor_rb_rows_kernel<true><<<grid, block, 0, h->st>>>(g, colour, shift, b_lo, b_hi, cp, omega, use_drift);
+				else sor_rb_rows_kernel<false><<<grid, block, 0, h->st>>>(g, colour, shift, b_lo, b_hi, cp, omega, use_drift);
+				h->lc.n++;
+			}
+			if (h->nranks > 1) {
+				FG_NCCL(ncclGroupStart());
+				if (has_up) {
+					FG_NCCL(ncclSend(row_hi, h->nf, ncclFloat, h->rank + 1, h->comm, h->st));
+					FG_NCCL(ncclRecv(h->recv_hi, h->nf, ncclFloat, h->rank + 1, h->comm, h->st));
+				}
+				if (has_down) {
+					FG_NCCL(ncclSend(row_lo, h->nf, ncclFloat, h->rank - 1, h->comm, h->st));
+					FG_NCCL(ncclRecv(h->recv_lo, h->nf, ncclFloat, h->rank - 1, h->comm, h->st));
+				}
+				FG_NCCL(ncclGroupEnd());
+				h->exchanges++;
+				// the upper rank's cells (a, j1) with (a+j1)%2==colour wrote row j1; the lower rank's cells (a, j0-1) with
+				// (a+j0-1)%2==colour wrote row j0
+				if (has_up) { merge_face_row_kernel<<<cdiv(h->nf, 256), 256, 0, h->st>>>(row_hi, h->recv_hi, h->nf, (colour + h->j1) & 1); h->lc.n++; }
+				if (has_down) { merge_face_row_kernel<<<cdiv(h->nf, 256), 256, 0, h->st>>>(row_lo, h->recv_lo, h->nf, (colour + h->j0 - 1) & 1); h->lc.n++; }
+			}
+		}
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+int sorshard_synchronize(SorShard* h) {
+	FG_CHECK(h, FLIPGPU_EINVAL, "null handle");
+	SDeviceGuard guard(h->device);
+	FG_CUDA(cudaStreamSynchronize(h->st));
+	return FLIPGPU_OK;
+}
+int sorshard_get_stream(SorShard* h, void** stream) {
+	FG_CHECK(h && stream, FLIPGPU_EINVAL, "null argument");
+	*stream = (void*)h->st;
+	return FLIPGPU_OK;
+}
+int sorshard_get_counters(SorShard* h, long long* launches, long long* exchanges) {
+	FG_CHECK(h && launches && exchanges, FLIPGPU_EINVAL, "null argument");
+	*launches = h->lc.n; *exchanges = h->exchanges;
+	return FLIPGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+"""Host-side plumbing for the slab-sharded path (one process per GPU, launched by torchrun).
+
+torch.distributed is used only to hand the NCCL communicator id from rank 0 to the other ranks and to gather
+results; the data path (halo rows) goes through the library's own NCCL communicator over NVLink."""
+import numpy as np
+
+
+def broadcast_unique_id(make_id=None):
+    """Rank 0 creates the 128-byte id (default: the library's ncclGetUniqueId), every rank returns the same bytes."""
+    import torch
+    import torch.distributed as dist
+    if make_id is None:
+        from .binding import nccl_unique_id as make_id
+    rank = dist.get_rank()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(make_id()), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def slab_partition(ns, nranks):
+    """[(j0, j1)] for every rank: contiguous, exhaustive, the library's rule (sorshard_slab)."""
+    return [(ns * r // nranks, ns * (r + 1) // nranks) for r in range(nranks)]
+
+
+def stitch_rows(parts):
+    """Concatenate per-rank own-row blocks (in rank order) back into the global (ns, nf) array."""
+    return np.concatenate(parts, axis=0)
