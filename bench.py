@@ -115,6 +115,61 @@ def run_cpu_reference(n_sample, steps, warmup):
                     ("integrate", "pushApart", "collide", "p2g", "density", "solve", "g2p", "colours"), ph)})
 
 
+
+def sharded_solver_bench(rank, world, local_rank, nf=8192, rows_per_rank=1024, iters=200, reps=3):
+    """Weak-scaling leg of BASELINE configs[4] (8192^2 with obstacle, 200 SOR sweeps: solver- and halo-bound): the grid is
+    cut into `world` slabs of rows_per_rank rows; the velocity halos (9 rows) are exchanged with both neighbours every 8 colour passes over
+    NCCL (9-row deep halo: one exchange per 8 colour passes).  8 ranks x 1024 rows == the 8192^2 grid of the config."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import simsandgames_b200 as sg
+    from simsandgames_b200 import parallel
+    ns = rows_per_rank * world
+    uid = parallel.broadcast_unique_id() if world > 1 else None
+    sh = sg.ShardedProjection(nf, ns, True, rank, world, unique_id=uid, device=local_rank)
+    j0, j1 = sh.w0, sh.w1
+    jj = np.arange(j0, j1, dtype=np.float32)[:, None]
+    ii = np.arange(nf, dtype=np.float32)[None, :]
+    s = np.ones((j1 - j0, nf), np.float32)
+    s[:, 0] = 0; s[:, -1] = 0
+    if j0 == 0: s[0] = 0
+    if j1 == ns: s[-1] = 0
+    disc = (ii + .5 - .75 * nf) ** 2 + (jj + .5 - .67 * ns) ** 2 < (.05 * nf) ** 2      # static obstacle (SURVEY S4 rule)
+    s[disc] = 0
+    rng = np.random.default_rng(1234 + rank)
+    sh.upload_rows("s", s, j0)
+    sh.upload_rows("cell_type", np.where(s == 0, 2, 0).astype(np.int32), j0)
+    sh.upload_rows("vel_fast", rng.normal(0, 1, s.shape).astype(np.float32) * s, j0)
+    sh.upload_rows("vel_slow", rng.normal(0, 1, s.shape).astype(np.float32) * s, j0)
+    stream = torch.cuda.ExternalStream(sh.stream, device=torch.device("cuda", local_rank))
+    cp = 1000.0 * (3.0 / nf) / (1 / 60.0 * 100 / nf)
+    sh.solve(iters, cp, 1.9)   # warm-up
+    sh.synchronize(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        sh.solve(iters, cp, 1.9)
+    e1.record(stream)
+    sh.synchronize(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches, exchanges = sh.counters()
+    updates = float(nf - 2) * float(ns - 2) * iters
+    out = {"workload": f"red-black SOR, {nf} x {ns} cells ({rows_per_rank} rows per GPU), {iters} sweeps, static disc obstacle (BASELINE configs[4] geometry at 8 GPUs)",
+           "n_gpus": world, "ms_per_solve": ms, "cell_updates_per_s": updates / (ms * 1e-3),
+           "alg_GBps_per_gpu": 36.0 * updates / world / (ms * 1e-3) / 1e9, "halo_exchanges_per_solve": exchanges // (reps + 1) if world > 1 else 0,
+           "halo_rows": sh.halo, "halo_bytes_per_exchange_per_neighbour": 2 * sh.halo * 4 * nf, "scaling": "weak"}
+    sh.close()
+    return out
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -236,6 +291,8 @@ def product_arm(args, rank, world, local_rank):
     e2e_ms_max = float(t.item())
     assert bool(torch.isfinite(h_pos[:1024]).all())
 
+    sim.close()
+    shard = sharded_solver_bench(rank, world, local_rank) if (world > 1 or args.with_shard_bench) else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -259,7 +316,7 @@ def product_arm(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD if N == BENCH_N else f"flip_fluid synthetic dam-break {N}^2 (non-default --grid)",
                    "grid": [nx, ny], "particles_per_gpu": P, "pressure_iters": iters, "separation_sweeps": 2,
                    "solver_order": "lexicographic (blocked wavefront, bit-identical to the reference order)", "colours": "off (render state, SURVEY 8d)",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent tanks, one per GPU (no halo exchange yet)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent tanks, one per GPU (particle sharding is not built yet; the slab-sharded solver with NCCL halo exchange is reported under sharded_solver)",
                    "reseed": f"state re-seeded (untimed, +{args.warmup} warm-up steps) every {SEG} timed steps: the dam-break rule diverges in the reference itself after ~15 steps (profiles/r1_stability.md)",
                    "l2": "working set ~4.7 GB per step >> 126 MB L2 (no flush needed)",
                    "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
@@ -278,6 +335,8 @@ def product_arm(args, rank, world, local_rank):
         "cell_updates_per_s": world * interior * iters / (solve_ms_per_step * 1e-3),
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
+    if shard is not None:
+        line["sharded_solver"] = shard
     if world == 1 and not args.no_cpu_baseline:
         n_sample = 1024
         r = run_cpu_reference(n_sample, 3, 0)
@@ -299,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="flipgpu", choices=["flipgpu", "reference"])
     ap.add_argument("--grid", type=int, default=BENCH_N, help="cells per side of the synthetic dam-break (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-shard-bench", action="store_true", help="also run the sharded-solver leg at N=1 (always run for N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

@@ -170,9 +170,9 @@ int euler_get_launch_count(EulerSim* sim, long long* launches);
 
 /* ------------------------------------------------------------------ multi-GPU: slab-sharded projection
  * One process per GPU.  The grid of nf x ns cells (nf = fast/contiguous axis) is cut into nranks slabs of rows
- * along the slow axis; rank r owns rows [j0,j1) = sorshard_slab(ns, r, nranks) plus one halo row on each side.
+ * along the slow axis; rank r owns rows [j0,j1) = sorshard_slab(ns, r, nranks) plus H halo rows on each side.
  * sorshard_solve runs red-black SOR sweeps (the update of flip_fluid.h:461-491 / fluid.h:110-135) with one
- * NCCL neighbour exchange of the shared face row per colour pass; results are bit-identical to the single-GPU
+ * NCCL neighbour exchange of H velocity rows every H-1 colour passes; results are bit-identical to the single-GPU
  * FLIP_SOLVER_RED_BLACK solve.  Rank 0 makes the communicator id, the host program broadcasts it (MPI,
  * torch.distributed, a file ...) and every rank passes it to sorshard_create. */
 typedef struct SorShard SorShard;
@@ -186,8 +186,8 @@ int flipgpu_nccl_unique_id(void* out128);                     /* 128 bytes (nccl
 void sorshard_slab(int ns, int rank, int nranks, int* j0, int* j1);
 int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void* unique_id128, int device, SorShard** out);
 int sorshard_destroy(SorShard* h);
-int sorshard_get_rows(SorShard* h, int* j0, int* j1);
-/* rows [j_start, j_start+n_rows) in global numbering, inside [j0-1, j1+1); host holds n_rows*nf elements */
+int sorshard_get_rows(SorShard* h, int* j0, int* j1, int* halo_rows);
+/* rows [j_start, j_start+n_rows) in global numbering, inside [j0-halo, j1+halo); host holds n_rows*nf elements */
 int sorshard_upload_rows(SorShard* h, int field, const void* host, int j_start, int n_rows);
 int sorshard_readback_rows(SorShard* h, int field, void* host, int j_start, int n_rows);
 int sorshard_solve(SorShard* h, int iters, float cp, float omega, int compensate_drift, float rest_density);

@@ -389,11 +389,13 @@ class ShardedProjection:
         _check(self._lib.sorshard_create(int(nf), int(ns), int(bool(x_fast)), int(rank), int(nranks), idbuf, int(device), C.byref(self._h)),
                "sorshard_create")
         self.nf, self.ns, self.rank, self.nranks = nf, ns, rank, nranks
-        self.j0, self.j1 = slab_rows(ns, rank, nranks)
-        self.w0, self.w1 = max(self.j0 - 1, 0), min(self.j1 + 1, ns)   # window incl. halo rows
+        j0, j1, halo = C.c_int(), C.c_int(), C.c_int()
+        _check(self._lib.sorshard_get_rows(self._h, C.byref(j0), C.byref(j1), C.byref(halo)), "sorshard_get_rows")
+        self.j0, self.j1, self.halo = j0.value, j1.value, halo.value
+        self.w0, self.w1 = max(self.j0 - self.halo, 0), min(self.j1 + self.halo, ns)   # window incl. halo rows
 
     def upload_window(self, name, global_array):
-        """Copy this rank's window rows [j0-1, j1+1) out of a full (ns, nf) host array."""
+        """Copy this rank's window rows [j0-halo, j1+halo) out of a full (ns, nf) host array."""
         fid, dt = SHARD_FIELDS[name]
         a = np.ascontiguousarray(np.asarray(global_array).reshape(self.ns, self.nf)[self.w0:self.w1], dtype=dt)
         _check(self._lib.sorshard_upload_rows(self._h, fid, a.ctypes.data_as(C.c_void_p), self.w0, self.w1 - self.w0), f"sorshard_upload_rows({name})")

@@ -1,17 +1,19 @@
-// Slab-sharded red-black SOR projection: one process per GPU, one slab of grid rows per rank, one
-// nearest-neighbour NCCL exchange per colour pass (stage "F9, every colour pass").
+// Slab-sharded red-black SOR projection: one process per GPU, one slab of grid rows per rank, nearest-neighbour
+// NCCL exchanges over NVLink (stage "F9").
 //
-// The grid is cut along the SLOW storage axis (rows are contiguous, so a halo row is one contiguous
-// message).  Rank r owns cell rows [j0, j1) and keeps one halo row on each side.  A cell update touches its
-// own faces and the high-side faces of its row (sor.cu), so the only data two ranks share is the face row
-// vel_s[., j1]: during colour pass c the lower rank's cells (a, j1-1) with (a+j1-1)%2==c write it at those
-// columns, the upper rank's cells (a, j1) with (a+j1)%2==c write it at the other columns.  After every pass
-// both ranks swap their copy of that row (ncclSend/ncclRecv in one group over NVLink) and keep, per column,
-// the value written by whoever owned the update -- so every cell update sees exactly the inputs it sees on
-// one GPU and the result is bit-identical to the single-GPU red-black solve (tests/test_gpu_multi.py).
+// The grid is cut along the SLOW storage axis (rows are contiguous, so a block of halo rows is one contiguous
+// message).  Rank r owns cell rows [j0, j1) and keeps H halo rows on each side.  Communication-avoiding deep
+// halo: after an exchange every local row is an exact copy of its owner's row; a colour pass then updates all
+// rows whose inputs are still exact -- own rows plus a halo band that shrinks by one row per pass -- so K = H-1
+// passes run back to back with no communication, the last one still covering own rows +-1 (which completes
+// the face row two slabs share).  The redundant halo cells perform exactly the updates their owner performs,
+// on identical inputs, so the result is bit-identical to the single-GPU red-black solve
+// (tests/test_gpu_multi.py) at 2*iters/K exchanges per solve instead of 2*iters (H=9: 50 instead of 400 for the
+// 200-sweep config), each carrying H rows of the two velocity fields.
 // The lexicographic wavefront is not sharded: its critical path crosses all slabs.
 #include <nccl.h>
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace fg {
@@ -55,22 +57,16 @@ __global__ void __launch_bounds__(256) sor_rb_rows_kernel(SorGrid g, int colour,
 	g.vel_s[c + nf] = vsp + ssp * pv;
 }
 
-// keep, per column, the neighbour's value where the neighbour's cells wrote the shared face row
-__global__ void merge_face_row_kernel(float* __restrict__ row, const float* __restrict__ recv, int nf, int parity) {
-	int a = blockIdx.x * blockDim.x + threadIdx.x;
-	if (a < nf && (a & 1) == parity) row[a] = recv[a];
-}
-
 }  // namespace fg
 
 using namespace fg;
 
 struct SorShard {
 	int nf = 0, ns = 0, rank = 0, nranks = 1, j0 = 0, j1 = 0, rows = 0, device = 0;
+	int halo = 9;  // H halo rows per side -> K = H-1 colour passes between exchanges
 	bool x_fast = true;
 	float *vel_f = nullptr, *vel_s = nullptr, *p = nullptr, *s = nullptr, *dens = nullptr, *d_rest = nullptr;
 	int* cell_type = nullptr;
-	float *recv_lo = nullptr, *recv_hi = nullptr;
 	ncclComm_t comm = nullptr;
 	cudaStream_t st = nullptr;
 	LaunchCounter lc;
@@ -115,7 +111,10 @@ void sorshard_slab(int ns, int rank, int nranks, int* j0, int* j1) {
 
 int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void* unique_id128, int device, SorShard** out) {
 	FG_CHECK(out && nf >= 3 && ns >= 3 && nranks >= 1 && rank >= 0 && rank < nranks, FLIPGPU_EINVAL, "sorshard_create: bad argument");
-	FG_CHECK(ns / nranks >= 2, FLIPGPU_EINVAL, "sorshard_create: %d rows over %d ranks leaves slabs thinner than 2 rows", ns, nranks);
+	int halo = 9;
+	if (const char* e = getenv("FLIPGPU_SHARD_HALO")) halo = std::max(2, atoi(e));
+	if (nranks == 1) halo = 1;
+	FG_CHECK(nranks == 1 || ns / nranks >= halo, FLIPGPU_EINVAL, "sorshard_create: %d rows over %d ranks leaves slabs thinner than the %d-row halo", ns, nranks, halo);
 	FG_CHECK(nranks == 1 || unique_id128, FLIPGPU_EINVAL, "sorshard_create: a NCCL unique id is required for %d ranks", nranks);
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -127,7 +126,8 @@ int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void
 	SorShard* h = new SorShard;
 	h->nf = nf; h->ns = ns; h->rank = rank; h->nranks = nranks; h->device = device; h->x_fast = x_fast != 0;
 	sorshard_slab(ns, rank, nranks, &h->j0, &h->j1);
-	h->rows = h->j1 - h->j0 + 2;  // own rows + one halo row on each side
+	h->halo = halo;
+	h->rows = h->j1 - h->j0 + 2 * halo;  // own rows + H halo rows on each side
 	SDeviceGuard guard(device);
 	FG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
 	size_t n = (size_t)nf * h->rows;
@@ -140,8 +140,6 @@ int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void
 	FG_CUDA(cudaMemsetAsync(h->cell_type, 0xff, n * 4, h->st));  // -1: not fluid until uploaded
 	FG_CUDA(cudaMalloc(&h->d_rest, 4));
 	FG_CUDA(cudaMemsetAsync(h->d_rest, 0, 4, h->st));
-	FG_CUDA(cudaMalloc(&h->recv_lo, (size_t)nf * 4));
-	FG_CUDA(cudaMalloc(&h->recv_hi, (size_t)nf * 4));
 	FG_CUDA(cudaStreamSynchronize(h->st));
 	if (nranks > 1) {
 		ncclUniqueId id;
@@ -157,29 +155,29 @@ int sorshard_destroy(SorShard* h) {
 	SDeviceGuard guard(h->device);
 	cudaStreamSynchronize(h->st);
 	if (h->comm) ncclCommDestroy(h->comm);
-	void* ptrs[] = {h->vel_f, h->vel_s, h->p, h->s, h->dens, h->cell_type, h->d_rest, h->recv_lo, h->recv_hi};
+	void* ptrs[] = {h->vel_f, h->vel_s, h->p, h->s, h->dens, h->cell_type, h->d_rest};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	cudaStreamDestroy(h->st);
 	delete h;
 	return FLIPGPU_OK;
 }
 
-int sorshard_get_rows(SorShard* h, int* j0, int* j1) {
-	FG_CHECK(h && j0 && j1, FLIPGPU_EINVAL, "null argument");
-	*j0 = h->j0; *j1 = h->j1;
+int sorshard_get_rows(SorShard* h, int* j0, int* j1, int* halo) {
+	FG_CHECK(h && j0 && j1 && halo, FLIPGPU_EINVAL, "null argument");
+	*j0 = h->j0; *j1 = h->j1; *halo = h->halo;
 	return FLIPGPU_OK;
 }
 
-// rows [j_start, j_start+n_rows) of a field, global row numbering; must lie inside own rows +- the halo row
+// rows [j_start, j_start+n_rows) of a field, global row numbering; must lie inside own rows +- the halo rows
 static int shard_copy(SorShard* h, int field, void* host, int j_start, int n_rows, bool to_device) {
 	FG_CHECK(h && host, FLIPGPU_EINVAL, "null argument");
 	size_t elem;
 	char* base = (char*)shard_field(h, field, &elem);
 	FG_CHECK(base, FLIPGPU_EINVAL, "sorshard: unknown field %d", field);
-	FG_CHECK(n_rows >= 0 && j_start >= h->j0 - 1 && j_start + n_rows <= h->j1 + 1 && j_start >= 0 && j_start + n_rows <= h->ns,
-	         FLIPGPU_EINVAL, "sorshard: rows [%d,%d) outside this rank's window [%d,%d)", j_start, j_start + n_rows, h->j0 - 1, h->j1 + 1);
+	FG_CHECK(n_rows >= 0 && j_start >= h->j0 - h->halo && j_start + n_rows <= h->j1 + h->halo && j_start >= 0 && j_start + n_rows <= h->ns,
+	         FLIPGPU_EINVAL, "sorshard: rows [%d,%d) outside this rank's window [%d,%d)", j_start, j_start + n_rows, h->j0 - h->halo, h->j1 + h->halo);
 	SDeviceGuard guard(h->device);
-	size_t off = (size_t)(j_start - (h->j0 - 1)) * h->nf * elem, bytes = (size_t)n_rows * h->nf * elem;
+	size_t off = (size_t)(j_start - (h->j0 - h->halo)) * h->nf * elem, bytes = (size_t)n_rows * h->nf * elem;
 	if (bytes) {
 		if (to_device) FG_CUDA(cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, h->st));
 		else FG_CUDA(cudaMemcpyAsync(host, base + off, bytes, cudaMemcpyDeviceToHost, h->st));
@@ -202,39 +200,43 @@ int sorshard_solve(SorShard* h, int iters, float cp, float omega, int drift, flo
 	SorGrid g;
 	g.nf = h->nf; g.ns = h->rows; g.vel_f = h->vel_f; g.vel_s = h->vel_s; g.p = h->p; g.s = h->s; g.cell_type = h->cell_type;
 	g.density = h->dens; g.rest = h->d_rest; g.x_fast = h->x_fast;
-	// local row l holds global row j0-1+l; interior global rows are 1..ns-2
-	const int b_lo = std::max(h->j0, 1) - (h->j0 - 1), b_hi = std::min(h->j1 - 1, h->ns - 2) - (h->j0 - 1);
-	const int shift = (h->j0 - 1) & 1;
+	// local row l holds global row j0-H+l; interior global rows are 1..ns-2
+	const int H = h->halo, K = std::max(H - 1, 1), base = h->j0 - H;
+	const int shift = ((base % 2) + 2) % 2;
 	const bool use_drift = drift != 0;
-	dim3 block(64, 4);
-	dim3 grid(cdiv((size_t)(h->nf + 1) / 2 + 1, block.x), cdiv((size_t)std::max(b_hi - b_lo + 1, 1), block.y));
-	float* row_hi = h->vel_s + (size_t)(h->rows - 1) * h->nf;  // global row j1  (halo above == the upper rank's first own row)
-	float* row_lo = h->vel_s + (size_t)1 * h->nf;              // global row j0  (own first row; the lower rank's halo above)
 	const bool has_up = h->rank + 1 < h->nranks, has_down = h->rank > 0;
+	dim3 block(64, 4);
+	const unsigned gx = cdiv((size_t)(h->nf + 1) / 2 + 1, block.x);
+	const size_t blk = (size_t)H * h->nf;  // one exchange block: H rows
+	int pass = 0;
 	for (int it = 0; it < iters; it++)
-		for (int colour = 0; colour < 2; colour++) {
-			if (b_hi >= b_lo) {
-				if (h->x_fast) sor_rb_rows_kernel<true><<<grid, block, 0, h->st>>>(g, colour, shift, b_lo, b_hi, cp, omega, use_drift);
-				else sor_rb_rows_kernel<false><<<grid, block, 0, h->st>>>(g, colour, shift, b_lo, b_hi, cp, omega, use_drift);
-				h->lc.n++;
-			}
-			if (h->nranks > 1) {
+		for (int colour = 0; colour < 2; colour++, pass++) {
+			const int m = h->nranks > 1 ? pass % K : 0;
+			if (h->nranks > 1 && m == 0) {
+				// refresh the halos: my H outermost own rows go to the neighbour's halo, its rows come into mine
+				float* fields[2] = {h->vel_f, h->vel_s};
 				FG_NCCL(ncclGroupStart());
-				if (has_up) {
-					FG_NCCL(ncclSend(row_hi, h->nf, ncclFloat, h->rank + 1, h->comm, h->st));
-					FG_NCCL(ncclRecv(h->recv_hi, h->nf, ncclFloat, h->rank + 1, h->comm, h->st));
-				}
-				if (has_down) {
-					FG_NCCL(ncclSend(row_lo, h->nf, ncclFloat, h->rank - 1, h->comm, h->st));
-					FG_NCCL(ncclRecv(h->recv_lo, h->nf, ncclFloat, h->rank - 1, h->comm, h->st));
+				for (float* f : fields) {
+					if (has_up) {
+						FG_NCCL(ncclSend(f + (size_t)(h->rows - 2 * H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
+						FG_NCCL(ncclRecv(f + (size_t)(h->rows - H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
+					}
+					if (has_down) {
+						FG_NCCL(ncclSend(f + (size_t)H * h->nf, blk, ncclFloat, h->rank - 1, h->comm, h->st));
+						FG_NCCL(ncclRecv(f, blk, ncclFloat, h->rank - 1, h->comm, h->st));
+					}
 				}
 				FG_NCCL(ncclGroupEnd());
 				h->exchanges++;
-				// the upper rank's cells (a, j1) with (a+j1)%2==colour wrote row j1; the lower rank's cells (a, j0-1) with
-				// (a+j0-1)%2==colour wrote row j0
-				if (has_up) { merge_face_row_kernel<<<cdiv(h->nf, 256), 256, 0, h->st>>>(row_hi, h->recv_hi, h->nf, (colour + h->j1) & 1); h->lc.n++; }
-				if (has_down) { merge_face_row_kernel<<<cdiv(h->nf, 256), 256, 0, h->st>>>(row_lo, h->recv_lo, h->nf, (colour + h->j0 - 1) & 1); h->lc.n++; }
 			}
+			// rows whose inputs are still exact: own rows plus a halo band that shrinks by one row per pass
+			int lo = has_down ? h->j0 - (H - 1) + m : h->j0, hi = has_up ? h->j1 + (H - 1) - m - 1 : h->j1 - 1;
+			lo = std::max(lo, 1); hi = std::min(hi, h->ns - 2);
+			if (hi < lo) continue;
+			dim3 grid(gx, cdiv((size_t)(hi - lo + 1), block.y));
+			if (h->x_fast) sor_rb_rows_kernel<true><<<grid, block, 0, h->st>>>(g, colour, shift, lo - base, hi - base, cp, omega, use_drift);
+			else sor_rb_rows_kernel<false><<<grid, block, 0, h->st>>>(g, colour, shift, lo - base, hi - base, cp, omega, use_drift);
+			h->lc.n++;
 		}
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
