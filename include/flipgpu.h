@@ -108,6 +108,11 @@ int flip_set_num_particles(FlipSim* sim, int n);
 int flip_upload(FlipSim* sim, int field, const void* host, size_t count);
 /* device -> host, reference layout and particle index order */
 int flip_readback(FlipSim* sim, int field, void* host, size_t count);
+/* particle_pos (caller order) -> pinned host memory without blocking: the PCIe copy runs on its own stream while the next
+ * flip_step computes; flip_readback_wait joins it.  This is the frame loop of main.cpp:160-182 with the draw of frame k
+ * overlapping the simulation of frame k+1. */
+int flip_readback_pos_async(FlipSim* sim, void* host, size_t count);
+int flip_readback_wait(FlipSim* sim);
 /* device equivalent of FluidUI::setObstacle (flip_fluid/src/main.cpp:95-126): rewrites s (and u,v inside
  * the disc) over 1<=i<nx-2, 1<=j<ny-2 (Q10) with the given obstacle velocity */
 int flip_set_obstacle(FlipSim* sim, float x, float y, float vx, float vy, float radius);

@@ -171,6 +171,13 @@ class FlipFluidGPU:
         fid, _ = FLIP_FIELDS[name]
         _check(self._lib.flip_upload(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"flip_upload({name})")
 
+    def readback_pos_async(self, ptr, count):
+        """particle_pos -> (pinned) host pointer on the copy stream; returns at once, join with readback_wait()."""
+        _check(self._lib.flip_readback_pos_async(self._h, C.c_void_p(ptr), C.c_size_t(count)), "flip_readback_pos_async")
+
+    def readback_wait(self):
+        _check(self._lib.flip_readback_wait(self._h), "flip_readback_wait")
+
     def set_obstacle(self, x, y, vx=0.0, vy=0.0, radius=0.15):
         """device equivalent of FluidUI::setObstacle, flip_fluid/src/main.cpp:95-126"""
         _check(self._lib.flip_set_obstacle(self._h, *[C.c_float(t) for t in (x, y, vx, vy, radius)]), "flip_set_obstacle")

@@ -648,6 +648,11 @@ struct FlipSim {
 	float* d_rest = nullptr;   // device scalar particle_rest_density
 	float* d_partials = nullptr;
 	float* h_pinned = nullptr;  // [0] rest mirror
+	// asynchronous readback of particle_pos (render thread consumes frame k while frame k+1 is computed)
+	cudaStream_t st_copy = nullptr;
+	cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
+	float2* staging = nullptr;
+	bool copy_pending = false;
 	SorWorkspace* ws = nullptr;
 	bool s_binary = true;       // every s[] is 0 or 1 (tracked on upload)
 	bool identity = true;       // slot order == caller order
@@ -958,6 +963,9 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	d.p_num_cells = d.p_num_x * d.p_num_y;
 	d.num_particles = 0;
 	FG_CUDA(cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking));
+	FG_CUDA(cudaStreamCreateWithFlags(&f->st_copy, cudaStreamNonBlocking));
+	FG_CUDA(cudaEventCreateWithFlags(&f->ev_staged, cudaEventDisableTiming));
+	FG_CUDA(cudaEventCreateWithFlags(&f->ev_copied, cudaEventDisableTiming));
 	size_t C = d.f_num_cells, M = std::max(d.max_particles, 1), H = d.p_num_cells;
 	float** grids[] = {&f->u, &f->v, &f->prev_u, &f->prev_v, &f->p, &f->s, &f->dens};
 	for (float** gp : grids) {
@@ -1005,6 +1013,10 @@ int flip_destroy(FlipSim* f) {
 	                f->first, f->tile_sum, f->d_rest, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
+	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
+	if (f->ev_staged) cudaEventDestroy(f->ev_staged);
+	if (f->ev_copied) cudaEventDestroy(f->ev_copied);
+	if (f->staging) cudaFree(f->staging);
 	sor_workspace_free(f->ws);
 	for (int r = 0; r < FlipSim::kEvRing; r++)
 		for (int i = 0; i <= FLIP_PH_COUNT; i++) if (f->ev[r][i]) cudaEventDestroy(f->ev[r][i]);
@@ -1095,6 +1107,35 @@ int flip_readback(FlipSim* f, int field, void* host, size_t count) {
 	FG_CUDA(cudaGetLastError());
 	if (count) FG_CUDA(cudaMemcpyAsync(host, srcp, count * 4, cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
+	return FLIPGPU_OK;
+}
+
+// particle_pos in caller order -> host, without blocking the caller or the simulation stream: the un-permute runs on
+// the simulation stream into a staging buffer, the PCIe copy on a second stream; flip_readback_wait() joins it.
+int flip_readback_pos_async(FlipSim* f, void* host, size_t count) {
+	FG_CHECK(f && host, FLIPGPU_EINVAL, "flip_readback_pos_async: null argument");
+	FG_CHECK(count == 2 * (size_t)f->d.num_particles, FLIPGPU_EINVAL, "flip_readback_pos_async: particle_pos holds %zu elements, asked for %zu",
+	         2 * (size_t)f->d.num_particles, count);
+	DeviceGuard guard(f->device);
+	int np = f->d.num_particles;
+	if (np == 0) return FLIPGPU_OK;
+	if (!f->staging) FG_CUDA(cudaMalloc(&f->staging, (size_t)std::max(f->d.max_particles, 1) * sizeof(float2)));
+	if (f->copy_pending) FG_CUDA(cudaStreamWaitEvent(f->st, f->ev_copied, 0));  // the staging buffer is still being read
+	if (f->identity) FG_CUDA(cudaMemcpyAsync(f->staging, f->pos[f->cur], (size_t)np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st));
+	else { k_scatter_to_caller<float2, 1><<<pgrid(f), kThreads, 0, f->st>>>(np, f->orig[f->cur], f->pos[f->cur], f->staging); f->lc.n++; }
+	FG_CUDA(cudaGetLastError());
+	FG_CUDA(cudaEventRecord(f->ev_staged, f->st));
+	FG_CUDA(cudaStreamWaitEvent(f->st_copy, f->ev_staged, 0));
+	FG_CUDA(cudaMemcpyAsync(host, f->staging, count * 4, cudaMemcpyDeviceToHost, f->st_copy));
+	FG_CUDA(cudaEventRecord(f->ev_copied, f->st_copy));
+	f->copy_pending = true;
+	return FLIPGPU_OK;
+}
+int flip_readback_wait(FlipSim* f) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	DeviceGuard guard(f->device);
+	if (f->copy_pending) FG_CUDA(cudaEventSynchronize(f->ev_copied));
+	f->copy_pending = false;
 	return FLIPGPU_OK;
 }
 

@@ -11,18 +11,49 @@
 // (tests/test_gpu_multi.py) at 2*iters/K exchanges per solve instead of 2*iters (H=9: 50 instead of 400 for the
 // 200-sweep config), each carrying H rows of the two velocity fields.
 // The lexicographic wavefront is not sharded: its critical path crosses all slabs.
-#include <nccl.h>
+#include <nccl.h>   // types only: NCCL is bound at run time (see NcclApi) so that single-GPU users never load it
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
 
 namespace fg {
 
+// NCCL through dlopen/dlsym.  Linking libnccl at build time would pull the system NCCL into every process that
+// loads this library; a host program that later loads a newer NCCL of the same SONAME (PyTorch bundles one) then
+// fails to resolve its symbols.  Binding lazily means: whichever libnccl.so.2 the process already holds is used,
+// and it is only loaded at all when a sharded object is created.
+struct NcclApi {
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+	if (g_nccl.ok) return FLIPGPU_OK;
+	void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) { fg::set_error("NCCL is not available: %s", dlerror()); return FLIPGPU_ENCCL; }
+#define FG_SYM(field, name) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); if (!g_nccl.field) { fg::set_error("NCCL symbol %s missing", name); return FLIPGPU_ENCCL; }
+	FG_SYM(GetUniqueId, "ncclGetUniqueId") FG_SYM(CommInitRank, "ncclCommInitRank") FG_SYM(CommDestroy, "ncclCommDestroy")
+	FG_SYM(GroupStart, "ncclGroupStart") FG_SYM(GroupEnd, "ncclGroupEnd") FG_SYM(Send, "ncclSend") FG_SYM(Recv, "ncclRecv")
+	FG_SYM(GetErrorString, "ncclGetErrorString")
+#undef FG_SYM
+	g_nccl.ok = true;
+	return FLIPGPU_OK;
+}
+
 #define FG_NCCL(call)                                                                          \
 	do {                                                                                       \
 		ncclResult_t r_ = (call);                                                              \
 		if (r_ != ncclSuccess) {                                                               \
-			fg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+			fg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, fg::g_nccl.GetErrorString(r_)); \
 			return FLIPGPU_ENCCL;                                                              \
 		}                                                                                      \
 	} while (0)
@@ -97,8 +128,9 @@ extern "C" {
 
 int flipgpu_nccl_unique_id(void* out128) {
 	FG_CHECK(out128, FLIPGPU_EINVAL, "null argument");
+	FG_TRY(load_nccl());
 	ncclUniqueId id;
-	FG_NCCL(ncclGetUniqueId(&id));
+	FG_NCCL(g_nccl.GetUniqueId(&id));
 	static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
 	memcpy(out128, &id, sizeof(id));
 	return FLIPGPU_OK;
@@ -144,7 +176,8 @@ int sorshard_create(int nf, int ns, int x_fast, int rank, int nranks, const void
 	if (nranks > 1) {
 		ncclUniqueId id;
 		memcpy(&id, unique_id128, sizeof(id));
-		FG_NCCL(ncclCommInitRank(&h->comm, nranks, id, rank));
+		FG_TRY(load_nccl());
+		FG_NCCL(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
 	}
 	*out = h;
 	return FLIPGPU_OK;
@@ -154,7 +187,7 @@ int sorshard_destroy(SorShard* h) {
 	if (!h) return FLIPGPU_OK;
 	SDeviceGuard guard(h->device);
 	cudaStreamSynchronize(h->st);
-	if (h->comm) ncclCommDestroy(h->comm);
+	if (h->comm) g_nccl.CommDestroy(h->comm);
 	void* ptrs[] = {h->vel_f, h->vel_s, h->p, h->s, h->dens, h->cell_type, h->d_rest};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	cudaStreamDestroy(h->st);
@@ -215,18 +248,18 @@ int sorshard_solve(SorShard* h, int iters, float cp, float omega, int drift, flo
 			if (h->nranks > 1 && m == 0) {
 				// refresh the halos: my H outermost own rows go to the neighbour's halo, its rows come into mine
 				float* fields[2] = {h->vel_f, h->vel_s};
-				FG_NCCL(ncclGroupStart());
+				FG_NCCL(g_nccl.GroupStart());
 				for (float* f : fields) {
 					if (has_up) {
-						FG_NCCL(ncclSend(f + (size_t)(h->rows - 2 * H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
-						FG_NCCL(ncclRecv(f + (size_t)(h->rows - H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
+						FG_NCCL(g_nccl.Send(f + (size_t)(h->rows - 2 * H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
+						FG_NCCL(g_nccl.Recv(f + (size_t)(h->rows - H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
 					}
 					if (has_down) {
-						FG_NCCL(ncclSend(f + (size_t)H * h->nf, blk, ncclFloat, h->rank - 1, h->comm, h->st));
-						FG_NCCL(ncclRecv(f, blk, ncclFloat, h->rank - 1, h->comm, h->st));
+						FG_NCCL(g_nccl.Send(f + (size_t)H * h->nf, blk, ncclFloat, h->rank - 1, h->comm, h->st));
+						FG_NCCL(g_nccl.Recv(f, blk, ncclFloat, h->rank - 1, h->comm, h->st));
 					}
 				}
-				FG_NCCL(ncclGroupEnd());
+				FG_NCCL(g_nccl.GroupEnd());
 				h->exchanges++;
 			}
 			// rows whose inputs are still exact: own rows plus a halo band that shrinks by one row per pass

@@ -474,3 +474,21 @@ def test_large_scene_properties(N):
     assert np.isfinite(mx) and rms < 1.0
     # moved, but by less than a few cells per step (CFL-matched dt)
     assert 0 < np.abs(pos.reshape(-1) - pos0).max() < 8 * h
+
+
+def test_async_readback_matches_blocking_readback():
+    import torch
+    sim, kw, g = sg.scenes.make_flip_tank("default")
+    P = sim.num_particles
+    frames = [torch.empty(2 * P, dtype=torch.float32).pin_memory() for _ in range(2)]
+    want = []
+    for k in range(4):
+        sim.simulate(**kw, n_steps=3, update_colors=False)
+        sim.readback_wait()
+        if k >= 2:
+            assert_bit_equal(frames[k % 2].numpy(), want[k - 2], f"frame {k - 2} (overwritten only after its wait)")
+        want.append(sim.readback("particle_pos").copy())
+        sim.readback_pos_async(frames[k % 2].data_ptr(), 2 * P)
+    sim.readback_wait()
+    assert_bit_equal(frames[1].numpy(), want[3], "last frame")
+    assert_bit_equal(frames[0].numpy(), want[2], "previous frame")
