@@ -446,3 +446,65 @@ class ShardedProjection:
             self.close()
         except Exception:
             pass
+
+
+class FlipFluidSharded(FlipFluidGPU):
+    """One rank's slab of a slab-sharded FlipFluid.  Grid arrays keep the global shape (only the rank's
+    window rows are current); particles are exchanged as (pos, vel, global id) triples."""
+
+    def __init__(self, density, width, height, spacing, particle_radius, max_local_particles, rank, nranks, unique_id=None, device=-1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        pr = _FlipParams(density, width, height, spacing, particle_radius, max_local_particles, device)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(self._lib.flip_create_sharded(C.byref(pr), int(rank), int(nranks), idbuf, C.byref(self._h)), "flip_create_sharded")
+        self._refresh()
+        self.rank, self.nranks = rank, nranks
+        self.j0, self.j1, self.halo, self.band, _ = self.shard_info()
+
+    def shard_info(self):
+        a, b, h, g, e = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_longlong()
+        _check(self._lib.flip_get_shard_info(self._h, C.byref(a), C.byref(b), C.byref(h), C.byref(g), C.byref(e)), "flip_get_shard_info")
+        return a.value, b.value, h.value, g.value, e.value
+
+    def owns(self, pos):
+        """mask of the particles (global (P,2) positions) whose cell row lies in this rank's slab"""
+        y = np.asarray(pos, np.float32).reshape(-1, 2)[:, 1]
+        row = np.clip((np.float32(self.f_inv_spacing) * y).astype(np.int32), 0, self.f_num_y - 1)
+        return (row >= self.j0) & (row < self.j1)
+
+    def upload_particles(self, pos, vel, ids):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1)
+        ids = np.ascontiguousarray(ids, np.int32).reshape(-1)
+        vp = None
+        if vel is not None:
+            vel = np.ascontiguousarray(vel, np.float32).reshape(-1)
+            vp = vel.ctypes.data_as(C.POINTER(C.c_float))
+        _check(self._lib.flip_upload_particles(self._h, pos.ctypes.data_as(C.POINTER(C.c_float)), vp,
+                                               ids.ctypes.data_as(C.POINTER(C.c_int)), int(ids.size)), "flip_upload_particles")
+        self._num_particles = int(ids.size)
+
+    def readback_particles(self):
+        cap = self.max_particles
+        pos = np.empty(2 * cap, np.float32); vel = np.empty(2 * cap, np.float32); ids = np.empty(cap, np.int32)
+        n = C.c_int()
+        _check(self._lib.flip_readback_particles(self._h, pos.ctypes.data_as(C.POINTER(C.c_float)), vel.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 ids.ctypes.data_as(C.POINTER(C.c_int)), cap, C.byref(n)), "flip_readback_particles")
+        k = n.value
+        return pos[:2 * k].copy(), vel[:2 * k].copy(), ids[:k].copy()
+
+    def upload_rows(self, name, rows, j_start):
+        fid, dt = FLIP_FIELDS[name]
+        a = np.ascontiguousarray(rows, dtype=dt).reshape(-1, self.f_num_x)
+        _check(self._lib.flip_upload_rows(self._h, fid, a.ctypes.data_as(C.c_void_p), int(j_start), a.shape[0]), f"flip_upload_rows({name})")
+
+    def readback_own_rows(self, name):
+        fid, dt = FLIP_FIELDS[name]
+        out = np.empty((self.j1 - self.j0, self.f_num_x), dt)
+        _check(self._lib.flip_readback_rows(self._h, fid, out.ctypes.data_as(C.c_void_p), self.j0, self.j1 - self.j0), f"flip_readback_rows({name})")
+        return out
+
+    def simulate(self, *args, **kw):
+        kw.setdefault("solver_order", RED_BLACK)
+        kw.setdefault("update_colors", False)
+        super().simulate(*args, **kw)

@@ -78,6 +78,7 @@ int sor_solve_strips(SorWorkspace** ws, const SorGrid& g, int iters, float cp, f
 // otherwise LEX_WAVEFRONT falls back to the unblocked diagonal kernel, same results).
 int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,
               cudaStream_t st, LaunchCounter* lc);
+void sor_rb_rows_launch(const SorGrid& g, int colour, int shift, int lo, int hi, float cp, float omega, bool drift, cudaStream_t st);
 int sor_residual(const SorGrid& g, bool drift, float* d_partials, int n_partials, float* h_out2, cudaStream_t st,
                  LaunchCounter* lc);
 

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <vector>
 #include "common.cuh"
+#include "nccl_shim.cuh"
 
 namespace fg {
 
@@ -32,6 +33,12 @@ struct Geo {  // constants every kernel needs, passed by value
 	int nx, ny, pnx, pny, np;
 	float h, inv_h, h2, r, p_inv;
 	float xmax_c, ymax_c;  // h*(nx-1), h*(ny-1): clamp bounds of the bilinear stencil (flip_fluid.h:301-302)
+	// Row windows.  One GPU: the whole grid.  Slab-sharded: the rows this rank keeps current (own rows + halo);
+	// particles that stray outside (invalid outer ghosts) are folded into the edge row so that every index stays
+	// inside the rows whose counters are cleared and scanned.
+	int gy0, gy1;          // grid rows [gy0, gy1)
+	int hy0, hy1;          // spatial-hash rows [hy0, hy1)
+	int ny0, ny1;          // node rows the P2G gather produces
 };
 
 // ------------------------------------------------------------------ device helpers
@@ -41,7 +48,7 @@ __device__ __forceinline__ float clampf(float a, float lo, float hi) { return a 
 // spatial-hash cell, flip_fluid.h:174-176
 __device__ __forceinline__ int hash_cell(const Geo& g, float x, float y, int* cx = nullptr, int* cy = nullptr) {
 	int xi = clampi((int)(x * g.p_inv), 0, g.pnx - 1);
-	int yi = clampi((int)(y * g.p_inv), 0, g.pny - 1);
+	int yi = clampi((int)(y * g.p_inv), g.hy0, g.hy1 - 1);
 	if (cx) { *cx = xi; *cy = yi; }
 	return xi + g.pnx * yi;
 }
@@ -330,8 +337,8 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 		float c0 = 0.f, c1 = 0.f, c2 = 0.f;
 		if (COLORS) { c0 = col_in[3 * (size_t)t]; c1 = col_in[3 * (size_t)t + 1]; c2 = col_in[3 * (size_t)t + 2]; }
 		int pxi = (int)(p.x * g.p_inv), pyi = (int)(p.y * g.p_inv);
-		int x0 = max(pxi - 1, 0), y0 = max(pyi - 1, 0);
-		int x1 = min(pxi + 1, g.pnx - 1), y1 = min(pyi + 1, g.pny - 1);
+		int x0 = max(pxi - 1, 0), y0 = max(pyi - 1, g.hy0);
+		int x1 = min(pxi + 1, g.pnx - 1), y1 = min(pyi + 1, g.hy1 - 1);
 		// the (up to) three window rows are three contiguous slot ranges; candidates are numbered through them
 		int ra[3], rn[3];
 #pragma unroll
@@ -414,12 +421,12 @@ __global__ void __launch_bounds__(kThreads) k_collide_mark(Geo g, float2* __rest
 		}
 		if (cell_type) {
 			int xi = clampi((int)(g.inv_h * p.x), 0, g.nx - 1);
-			int yi = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
+			int yi = clampi((int)(g.inv_h * p.y), g.gy0, g.gy1 - 1);
 			int c = xi + g.nx * yi;
 			if (cell_type[c] == AIR_CELL) cell_type[c] = FLUID_CELL;  // all racing writers store the same value
 			// base cell of the stencil, exactly as :301-308 (clamped position, cell-centred offset)
 			float x = clampf(p.x, g.h, g.xmax_c), y = clampf(p.y, g.h, g.ymax_c);
-			int x0 = clampi((int)(g.inv_h * (x - g.h2)), 0, g.nx - 1), y0 = clampi((int)(g.inv_h * (y - g.h2)), 0, g.ny - 1);
+			int x0 = clampi((int)(g.inv_h * (x - g.h2)), 0, g.nx - 1), y0 = clampi((int)(g.inv_h * (y - g.h2)), g.gy0, g.gy1 - 1);
 			int key = x0 + g.nx * y0;
 			gkeys[t] = key;
 			atomicAdd(gcount + key, 1);  // integer histogram: order-independent
@@ -473,11 +480,11 @@ __global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict
                                                     float* __restrict__ prev_v, float* __restrict__ dens,
                                                     float* __restrict__ p) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	int j = blockIdx.y * blockDim.y + threadIdx.y;
-	if (i >= g.nx || j >= g.ny) return;
+	int j = g.ny0 + blockIdx.y * blockDim.y + threadIdx.y;
+	if (i >= g.nx || j >= g.ny1) return;
 	float su = 0.f, sv = 0.f, sw = 0.f;
 	int cx0 = max(i - 1, 0);
-	for (int cy = max(j - 1, 0); cy <= j; cy++) {
+	for (int cy = max(j - 1, g.gy0); cy <= j; cy++) {
 		int a = gfirst[cx0 + g.nx * cy], b = gfirst[i + g.nx * cy + 1];
 		for (int k = a; k < b; k++) {
 			int t = gidx[k];
@@ -626,6 +633,52 @@ __global__ void __launch_bounds__(256) k_set_obstacle(Geo g, float x, float y, f
 	s[c] = sv;
 }
 
+
+// ------------------------------------------------------------------ slab sharding: particle ownership and ghosts
+// Ownership is by position: a particle belongs to the rank whose slab holds the grid row of its cell.  At the start
+// of a step every rank keeps the particles it owns (out of everything it simulated last step, ghosts included: a
+// particle that crossed the boundary was a valid ghost on its new owner) and copies the ones within `band` rows of a
+// slab boundary into the neighbour's send buffer.  Slot order does not matter: the counting sort orders by
+// (hash cell, global id), which is the same relative order on any partition.
+struct ShardPack {
+	float2* pos; float2* vel; int* id;
+};
+__global__ void __launch_bounds__(kThreads) k_shard_classify(Geo g, int j0, int j1, int band, int has_down, int has_up,
+                                                             const float2* __restrict__ pos, const float2* __restrict__ vel,
+                                                             const int* __restrict__ id, ShardPack keep, ShardPack down, ShardPack up,
+                                                             int* __restrict__ counters /* [0] keep [1] down [2] up */, int cap_send) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		float2 p = pos[t];
+		int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
+		if (row < j0 || row >= j1) continue;
+		float2 v = vel[t];
+		int gid = id[t];
+		int k = atomicAdd(counters + 0, 1);
+		keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
+		if (has_down && row < j0 + band) {
+			int m = atomicAdd(counters + 1, 1);
+			if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = gid; }
+		}
+		if (has_up && row >= j1 - band) {
+			int m = atomicAdd(counters + 2, 1);
+			if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = gid; }
+		}
+	}
+}
+
+
+// rest-density latch across slabs: per-rank (sum, count) over own rows, summed over ranks (flip_fluid.h:321-332)
+__global__ void k_rest_pair(int n_partials, const float* __restrict__ partials, const float* __restrict__ rest, float* __restrict__ pair) {
+	if (threadIdx.x != 0) return;
+	double s = 0.0, cnt = 0.0;
+	if (*rest == 0.f)
+		for (int i = 0; i < n_partials; i++) { s += partials[2 * i]; cnt += partials[2 * i + 1]; }
+	pair[0] = (float)s; pair[1] = (float)cnt;
+}
+__global__ void k_rest_from_pair(const float* __restrict__ pair, float* __restrict__ rest) {
+	if (threadIdx.x == 0 && *rest == 0.f && pair[1] > 0.f) *rest = pair[0] / pair[1];
+}
+
 }  // namespace fg
 
 // =================================================================== host side
@@ -654,6 +707,18 @@ struct FlipSim {
 	float2* staging = nullptr;
 	bool copy_pending = false;
 	SorWorkspace* ws = nullptr;
+	// slab sharding (flip_create_sharded): rank owns grid rows [j0, j1); arrays keep the global size, only the window is processed
+	bool sharded = false;
+	int rank = 0, nranks = 1, j0 = 0, j1 = 0, halo = 9, band = 6;
+	int gy0 = 0, gy1 = 0, hy0 = 0, hy1 = 0;
+	ncclComm_t comm = nullptr;
+	float2 *send_pos[2] = {nullptr, nullptr}, *send_vel[2] = {nullptr, nullptr};
+	int* send_id[2] = {nullptr, nullptr};
+	int cap_send = 0;
+	int* d_counters = nullptr;   // [0] keep [1] down [2] up [3] from-down [4] from-up
+	int* h_counters = nullptr;   // pinned mirror
+	int n_owned = 0;
+	long long exchanges = 0;
 	bool s_binary = true;       // every s[] is 0 or 1 (tracked on upload)
 	bool identity = true;       // slot order == caller order
 	bool bins_valid = false;
@@ -676,6 +741,8 @@ Geo geo(const FlipSim* f) {
 	g.h = f->d.h; g.inv_h = f->d.f_inv_spacing; g.h2 = .5f * f->d.h; g.r = f->d.particle_radius; g.p_inv = f->d.p_inv_spacing;
 	g.xmax_c = f->d.h * (float)(f->d.f_num_x - 1);
 	g.ymax_c = f->d.h * (float)(f->d.f_num_y - 1);
+	if (f->sharded) { g.gy0 = f->gy0; g.gy1 = f->gy1; g.hy0 = f->hy0; g.hy1 = f->hy1; g.ny0 = f->j0; g.ny1 = f->j1; }
+	else { g.gy0 = 0; g.gy1 = g.ny; g.hy0 = 0; g.hy1 = g.pny; g.ny0 = 0; g.ny1 = g.ny; }
 	return g;
 }
 unsigned pgrid(const FlipSim* f) { return wave_grid((size_t)std::max(f->d.num_particles, 1), kThreads); }
@@ -749,12 +816,13 @@ void running_sum(FlipSim* f, const int* count, int n, int* first) {
 // F2: counting sort into hash-cell order.  keys/count must already hold this step's histogram.
 int bin_from_histogram(FlipSim* f) {
 	Geo g = geo(f);
-	int Hc = f->d.p_num_cells, np = g.np;
-	running_sum(f, f->count, Hc, f->first);
+	const size_t hoff = (size_t)g.pnx * g.hy0;
+	int Hc = g.pnx * (g.hy1 - g.hy0), np = g.np;
+	running_sum(f, f->count + hoff, Hc, f->first + hoff);
 	int c = f->cur, n = 1 - c;
 	if (np > 0) {
 		k_fill<<<pgrid(f), kThreads, 0, f->st>>>(np, f->keys, f->orig[c], f->first, f->src, f->orig[n]);
-		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count, f->first, f->src, f->orig[n]);
+		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count + hoff, f->first + hoff, f->src, f->orig[n]);
 		if (f->col[0])
 			k_reorder<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n]);
 		else
@@ -771,7 +839,7 @@ int bin_from_histogram(FlipSim* f) {
 int integrate_and_bin(FlipSim* f, bool integrate, bool bin, float dt, float gravity) {
 	Geo g = geo(f);
 	int c = f->cur;
-	if (bin) FG_CUDA(cudaMemsetAsync(f->count, 0, (size_t)f->d.p_num_cells * 4, f->st));
+	if (bin) FG_CUDA(cudaMemsetAsync(f->count + (size_t)g.pnx * g.hy0, 0, (size_t)g.pnx * (g.hy1 - g.hy0) * 4, f->st));
 	if (g.np > 0) {
 		if (integrate && bin) k_integrate_bin<true, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], dt, gravity, f->keys, f->count);
 		else if (integrate) k_integrate_bin<true, false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], dt, gravity, f->keys, f->count);
@@ -811,11 +879,12 @@ int separate(FlipSim* f, int iters, bool colors) {
 
 int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad) {
 	Geo g = geo(f);
-	int c = f->cur, C = f->d.f_num_cells;
+	const size_t goff = (size_t)g.nx * g.gy0;
+	int c = f->cur, C = g.nx * (g.gy1 - g.gy0);
 	if (mark) {
-		k_cell_type_from_s<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->s, f->cell_type);
+		k_cell_type_from_s<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->s + goff, f->cell_type + goff);
 		f->lc.n++;
-		FG_CUDA(cudaMemsetAsync(f->gcount, 0, (size_t)C * 4, f->st));
+		FG_CUDA(cudaMemsetAsync(f->gcount + goff, 0, (size_t)C * 4, f->st));
 	}
 	if (g.np > 0) {
 		int* ct = mark ? f->cell_type : nullptr;
@@ -824,10 +893,10 @@ int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float 
 		f->lc.n++;
 	}
 	if (mark) {  // index-only counting sort by stencil base cell: gidx (= src) lists the slots of every grid cell
-		running_sum(f, f->gcount, C, f->gfirst);
+		running_sum(f, f->gcount + goff, C, f->gfirst + goff);
 		if (g.np > 0) {
 			k_fill_grid<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->keys, f->gfirst, f->src);
-			k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount, f->gfirst, f->src);
+			k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src);
 			f->lc.n += 2;
 		}
 	}
@@ -835,15 +904,19 @@ int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float 
 	return FLIPGPU_OK;
 }
 
+int shard_rest_latch(FlipSim* f);
+
 int p2g(FlipSim* f) {
 	Geo g = geo(f);
 	int c = f->cur;
 	dim3 block(32, 8);
-	dim3 grid(cdiv(g.nx, block.x), cdiv(g.ny, block.y));
+	dim3 grid(cdiv(g.nx, block.x), cdiv(g.ny1 - g.ny0, block.y));
 	k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
 	                                        f->prev_u, f->prev_v, f->dens, f->p);
 	f->lc.n++;
-	if (!f->rest_seen) {
+	if (!f->rest_seen && f->sharded) {
+		FG_TRY(shard_rest_latch(f));
+	} else if (!f->rest_seen) {
 		k_rest_partials<<<kPartials, 256, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest, f->d_partials);
 		k_rest_latch<<<1, 32, 0, f->st>>>(kPartials, f->d_partials, f->d_rest);
 		f->lc.n += 2;
@@ -869,6 +942,150 @@ int g2p(FlipSim* f, float flip_ratio) {
 	k_g2p<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio);
 	f->lc.n++;
 	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+
+// ------------------------------------------------------------------ slab-sharded step
+int shard_rest_latch(FlipSim* f) {
+	const size_t off = (size_t)f->d.f_num_x * f->j0;
+	const int n = f->d.f_num_x * (f->j1 - f->j0);
+	k_rest_partials<<<kPartials, 256, 0, f->st>>>(n, f->cell_type + off, f->dens + off, f->d_rest, f->d_partials);
+	float* pair = f->d_partials + 2 * kPartials;
+	k_rest_pair<<<1, 32, 0, f->st>>>(kPartials, f->d_partials, f->d_rest, pair);
+	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(pair, pair, 2, ncclFloat, ncclSum, f->comm, f->st));
+	k_rest_from_pair<<<1, 32, 0, f->st>>>(pair, f->d_rest);
+	f->lc.n += 3;
+	FG_CUDA(cudaMemcpyAsync(f->h_pinned, f->d_rest, sizeof(float), cudaMemcpyDeviceToHost, f->st));
+	return FLIPGPU_OK;
+}
+
+// swap `rows` rows at both slab boundaries: my outermost own rows go into the neighbour's halo and vice versa.
+// Arrays keep the global size, so a row sits at the same offset on every rank.
+int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows) {
+	if (f->nranks == 1) return FLIPGPU_OK;
+	const size_t nx = f->d.f_num_x, blk = nx * rows;
+	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
+	FG_NCCL(g_nccl.GroupStart());
+	for (int k = 0; k < n_fields; k++) {
+		float* a = (float*)fields[k];
+		if (has_up) {
+			FG_NCCL(g_nccl.Send(a + nx * (f->j1 - rows), blk, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(a + nx * f->j1, blk, ncclFloat, f->rank + 1, f->comm, f->st));
+		}
+		if (has_down) {
+			FG_NCCL(g_nccl.Send(a + nx * f->j0, blk, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(a + nx * (f->j0 - rows), blk, ncclFloat, f->rank - 1, f->comm, f->st));
+		}
+	}
+	FG_NCCL(g_nccl.GroupEnd());
+	f->exchanges++;
+	return FLIPGPU_OK;
+}
+
+// keep what this rank owns, refresh the ghosts from both neighbours
+int shard_exchange_particles(FlipSim* f) {
+	Geo g = geo(f);
+	const int c = f->cur, n = 1 - c;
+	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
+	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
+	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
+	if (g.np > 0) {
+		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, f->band, has_down, has_up, f->pos[c], f->vel[c], f->orig[c], keep,
+		                                                    down, up, f->d_counters, f->cap_send);
+		f->lc.n++;
+	}
+	// tell each neighbour how many ghosts are coming (device-to-device ints), then read all five counters once
+	if (f->nranks > 1) {
+		FG_NCCL(g_nccl.GroupStart());
+		if (has_down) {
+			FG_NCCL(g_nccl.Send(f->d_counters + 1, 1, ncclInt, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->d_counters + 3, 1, ncclInt, f->rank - 1, f->comm, f->st));
+		}
+		if (has_up) {
+			FG_NCCL(g_nccl.Send(f->d_counters + 2, 1, ncclInt, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->d_counters + 4, 1, ncclInt, f->rank + 1, f->comm, f->st));
+		}
+		FG_NCCL(g_nccl.GroupEnd());
+	}
+	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	const int n_keep = f->h_counters[0], n_down = f->h_counters[1], n_up = f->h_counters[2], from_down = f->h_counters[3], from_up = f->h_counters[4];
+	FG_CHECK(n_down <= f->cap_send && n_up <= f->cap_send, FLIPGPU_ESTATE, "shard: %d/%d ghost particles exceed the send capacity %d", n_down, n_up, f->cap_send);
+	FG_CHECK((long long)n_keep + from_down + from_up <= f->d.max_particles, FLIPGPU_ESTATE, "shard: %d owned + %d + %d ghosts exceed max_particles %d",
+	         n_keep, from_down, from_up, f->d.max_particles);
+	if (f->nranks > 1) {
+		FG_NCCL(g_nccl.GroupStart());
+		int at = n_keep;
+		if (has_down) {
+			FG_NCCL(g_nccl.Send(f->send_pos[0], 2 * (size_t)n_down, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Send(f->send_vel[0], 2 * (size_t)n_down, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Send(f->send_id[0], (size_t)n_down, ncclInt, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->pos[n] + at, 2 * (size_t)from_down, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->vel[n] + at, 2 * (size_t)from_down, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->orig[n] + at, (size_t)from_down, ncclInt, f->rank - 1, f->comm, f->st));
+			at += from_down;
+		}
+		if (has_up) {
+			FG_NCCL(g_nccl.Send(f->send_pos[1], 2 * (size_t)n_up, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Send(f->send_vel[1], 2 * (size_t)n_up, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Send(f->send_id[1], (size_t)n_up, ncclInt, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->pos[n] + at, 2 * (size_t)from_up, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->vel[n] + at, 2 * (size_t)from_up, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->orig[n] + at, (size_t)from_up, ncclInt, f->rank + 1, f->comm, f->st));
+		}
+		FG_NCCL(g_nccl.GroupEnd());
+		f->exchanges++;
+	}
+	f->cur = n;
+	f->n_owned = n_keep;
+	f->d.num_particles = n_keep + from_down + from_up;
+	f->identity = false;
+	f->bins_valid = false;
+	return FLIPGPU_OK;
+}
+
+// red-black sweeps with the communication-avoiding deep halo of sor_shard.cu, on this handle's (global-size) arrays
+int shard_solve(FlipSim* f, int iters, float cp, float omega, bool drift) {
+	SorGrid g = sor_view(f);
+	const int H = f->halo, K = std::max(H - 1, 1);
+	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
+	void* vel[2] = {f->u, f->v};
+	int pass = 0;
+	for (int it = 0; it < iters; it++)
+		for (int colour = 0; colour < 2; colour++, pass++) {
+			const int m = f->nranks > 1 ? pass % K : 0;
+			if (f->nranks > 1 && m == 0) FG_TRY(shard_exchange_rows(f, vel, 2, H));
+			int lo = has_down ? f->j0 - (H - 1) + m : f->j0, hi = has_up ? f->j1 + (H - 1) - m - 1 : f->j1 - 1;
+			lo = std::max(lo, 1); hi = std::min(hi, f->d.f_num_y - 2);
+			if (hi < lo) continue;
+			sor_rb_rows_launch(g, colour, 0, lo, hi, cp, omega, drift && g.density && g.rest, f->st);
+			f->lc.n++;
+		}
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+int shard_step(FlipSim* f, const FlipStepParams* sp) {
+	FG_CHECK(sp->solver_order == FLIP_SOLVER_RED_BLACK, FLIPGPU_EINVAL, "a sharded simulation runs the red-black order (the lexicographic wavefront does not shard)");
+	FG_CHECK(!sp->update_colors, FLIPGPU_EINVAL, "render-state colours are not kept in sharded mode");
+	const float cp = f->d.density * f->d.h / sp->dt;
+	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
+	FG_TRY(shard_exchange_particles(f));                                   // ownership by position + ghost refresh
+	FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));         // owned + ghosts
+	if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, false));
+	FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
+	FG_TRY(p2g(f));                                                        // own node rows
+	{	// the rows next to the slab come from their owners: post-P2G fields, cell types, densities, s
+		void* fields[] = {f->u, f->v, f->prev_u, f->prev_v, f->dens, f->cell_type, f->s};
+		FG_TRY(shard_exchange_rows(f, fields, 7, f->halo));
+	}
+	FG_TRY(shard_solve(f, sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0));
+	{	// post-solve velocities (and the pressure) of the halo rows, for the G2P of particles near the boundary
+		void* fields[] = {f->u, f->v, f->p};
+		FG_TRY(shard_exchange_rows(f, fields, 3, f->halo));
+	}
+	FG_TRY(g2p(f, sp->flip_ratio));
 	return FLIPGPU_OK;
 }
 
@@ -1012,6 +1229,10 @@ int flip_destroy(FlipSim* f) {
 	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->gcount, f->gfirst, f->count,
 	                f->first, f->tile_sum, f->d_rest, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
+	if (f->comm) g_nccl.CommDestroy(f->comm);
+	for (int k = 0; k < 2; k++) { cudaFree(f->send_pos[k]); cudaFree(f->send_vel[k]); cudaFree(f->send_id[k]); }
+	cudaFree(f->d_counters);
+	if (f->h_counters) cudaFreeHost(f->h_counters);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
 	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
 	if (f->ev_staged) cudaEventDestroy(f->ev_staged);
@@ -1034,6 +1255,7 @@ int flip_get_dims(FlipSim* f, FlipDims* dims) {
 int flip_set_num_particles(FlipSim* f, int n) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(n >= 0 && n <= f->d.max_particles, FLIPGPU_EINVAL, "num_particles %d outside [0,%d]", n, f->d.max_particles);
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "sharded simulation: the particle count follows flip_upload_particles");
 	DeviceGuard guard(f->device);
 	FG_TRY(unsort(f));
 	f->d.num_particles = n;
@@ -1048,6 +1270,7 @@ int flip_upload(FlipSim* f, int field, const void* host, size_t count) {
 	size_t want = field_count(f, field);
 	FG_CHECK(count == want, FLIPGPU_EINVAL, "flip_upload: field %d takes %zu elements, got %zu", field, want, count);
 	void* dst = grid_field_ptr(f, field);
+	FG_CHECK(dst || !f->sharded, FLIPGPU_ESTATE, "sharded simulation: use flip_upload_particles / flip_upload_rows");
 	if (!dst) {
 		switch (field) {
 			case FLIP_PARTICLE_POS: FG_TRY(unsort(f)); dst = f->pos[f->cur]; f->bins_valid = false; break;
@@ -1077,6 +1300,7 @@ int flip_readback(FlipSim* f, int field, void* host, size_t count) {
 	size_t want = field_count(f, field);
 	FG_CHECK(count == want, FLIPGPU_EINVAL, "flip_readback: field %d holds %zu elements, asked for %zu", field, want, count);
 	const void* srcp = grid_field_ptr(f, field);
+	FG_CHECK(srcp || !f->sharded, FLIPGPU_ESTATE, "sharded simulation: use flip_readback_particles / flip_readback_rows");
 	int np = f->d.num_particles, c = f->cur, n = 1 - c;
 	unsigned gr = pgrid(f);
 	if (!srcp) {
@@ -1157,6 +1381,10 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 	FG_CHECK(sp->num_pressure_iters >= 0 && sp->num_particle_iters >= 0 && sp->dt > 0, FLIPGPU_EINVAL, "flip_step: bad params");
 	DeviceGuard guard(f->device);
 	const float cp = f->d.density * f->d.h / sp->dt;  // flip_fluid.h:456
+	if (f->sharded) {
+		for (int k = 0; k < n_steps; k++) FG_TRY(shard_step(f, sp));
+		return FLIPGPU_OK;
+	}
 	for (int k = 0; k < n_steps; k++) {
 		if (f->timings_on) collect_slot(f, f->ev_slot);
 		if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
@@ -1184,6 +1412,116 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 	}
 	return FLIPGPU_OK;
 }
+
+
+// ------------------------------------------------------------------ slab-sharded FLIP
+int flip_create_sharded(const FlipParams* pr, int rank, int nranks, const void* unique_id128, FlipSim** out) {
+	FG_CHECK(pr && out && nranks >= 1 && rank >= 0 && rank < nranks, FLIPGPU_EINVAL, "flip_create_sharded: bad argument");
+	FG_CHECK(nranks == 1 || unique_id128, FLIPGPU_EINVAL, "flip_create_sharded: a NCCL unique id is required for %d ranks", nranks);
+	FlipSim* f = nullptr;
+	FG_TRY(flip_create(pr, &f));
+	DeviceGuard guard(f->device);
+	const int ny = f->d.f_num_y;
+	f->sharded = true; f->rank = rank; f->nranks = nranks;
+	f->j0 = (int)((long long)ny * rank / nranks);
+	f->j1 = (int)((long long)ny * (rank + 1) / nranks);
+	if (nranks > 1 && f->j1 - f->j0 < f->halo + 1) {
+		flip_destroy(f);
+		fg::set_error("flip_create_sharded: %d rows over %d ranks leaves slabs thinner than the %d-row halo", ny, nranks, f->halo);
+		return FLIPGPU_EINVAL;
+	}
+	f->gy0 = std::max(f->j0 - f->halo, 0); f->gy1 = std::min(f->j1 + f->halo, ny);
+	f->hy0 = std::max((int)((float)f->gy0 * f->d.h * f->d.p_inv_spacing) - 1, 0);
+	f->hy1 = std::min((int)((float)f->gy1 * f->d.h * f->d.p_inv_spacing) + 2, f->d.p_num_y);
+	f->cap_send = std::max(f->d.max_particles / 3, 1024);
+	for (int k = 0; k < 2; k++) {
+		FG_CUDA(cudaMalloc(&f->send_pos[k], (size_t)f->cap_send * sizeof(float2)));
+		FG_CUDA(cudaMalloc(&f->send_vel[k], (size_t)f->cap_send * sizeof(float2)));
+		FG_CUDA(cudaMalloc(&f->send_id[k], (size_t)f->cap_send * 4));
+	}
+	FG_CUDA(cudaMalloc(&f->d_counters, 8 * sizeof(int)));
+	FG_CUDA(cudaMallocHost(&f->h_counters, 8 * sizeof(int)));
+	f->d.num_particles = 0;
+	f->identity = false;
+	if (nranks > 1) {
+		FG_TRY(load_nccl());
+		ncclUniqueId id;
+		memcpy(&id, unique_id128, sizeof(id));
+		FG_NCCL(g_nccl.CommInitRank(&f->comm, nranks, id, rank));
+	}
+	*out = f;
+	return FLIPGPU_OK;
+}
+
+int flip_get_shard_info(FlipSim* f, int* j0, int* j1, int* halo_rows, int* ghost_band_rows, long long* exchanges) {
+	FG_CHECK(f && j0 && j1 && halo_rows && ghost_band_rows && exchanges, FLIPGPU_EINVAL, "null argument");
+	FG_CHECK(f->sharded, FLIPGPU_ESTATE, "not a sharded simulation");
+	*j0 = f->j0; *j1 = f->j1; *halo_rows = f->halo; *ghost_band_rows = f->band; *exchanges = f->exchanges;
+	return FLIPGPU_OK;
+}
+
+// this rank's particles with their GLOBAL caller indices (any order); replaces whatever the rank held
+int flip_upload_particles(FlipSim* f, const float* pos, const float* vel, const int* ids, int n) {
+	FG_CHECK(f && (n == 0 || (pos && ids)), FLIPGPU_EINVAL, "flip_upload_particles: null argument");
+	FG_CHECK(f->sharded, FLIPGPU_ESTATE, "flip_upload_particles is for sharded simulations");
+	FG_CHECK(n >= 0 && n <= f->d.max_particles, FLIPGPU_EINVAL, "flip_upload_particles: %d particles exceed the local capacity %d", n, f->d.max_particles);
+	DeviceGuard guard(f->device);
+	const int c = f->cur;
+	if (n) {
+		FG_CUDA(cudaMemcpyAsync(f->pos[c], pos, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, f->st));
+		if (vel) FG_CUDA(cudaMemcpyAsync(f->vel[c], vel, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, f->st));
+		else FG_CUDA(cudaMemsetAsync(f->vel[c], 0, (size_t)n * sizeof(float2), f->st));
+		FG_CUDA(cudaMemcpyAsync(f->orig[c], ids, (size_t)n * 4, cudaMemcpyHostToDevice, f->st));
+	}
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	f->d.num_particles = n; f->n_owned = n; f->bins_valid = false; f->identity = false;
+	return FLIPGPU_OK;
+}
+
+// the particles this rank OWNS now (by position), with their global indices; *n_out = how many
+int flip_readback_particles(FlipSim* f, float* pos, float* vel, int* ids, int capacity, int* n_out) {
+	FG_CHECK(f && n_out, FLIPGPU_EINVAL, "flip_readback_particles: null argument");
+	FG_CHECK(f->sharded, FLIPGPU_ESTATE, "flip_readback_particles is for sharded simulations");
+	DeviceGuard guard(f->device);
+	Geo g = geo(f);
+	const int c = f->cur, n = 1 - c;
+	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
+	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, none{nullptr, nullptr, nullptr};
+	if (g.np > 0) {
+		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, 0, 0, 0, f->pos[c], f->vel[c], f->orig[c], keep, none, none, f->d_counters, 0);
+		f->lc.n++;
+	}
+	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	const int k = f->h_counters[0];
+	*n_out = k;
+	FG_CHECK(k <= capacity, FLIPGPU_EINVAL, "flip_readback_particles: %d owned particles, capacity %d", k, capacity);
+	if (k) {
+		if (pos) FG_CUDA(cudaMemcpyAsync(pos, f->pos[n], (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, f->st));
+		if (vel) FG_CUDA(cudaMemcpyAsync(vel, f->vel[n], (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, f->st));
+		if (ids) FG_CUDA(cudaMemcpyAsync(ids, f->orig[n], (size_t)k * 4, cudaMemcpyDeviceToHost, f->st));
+	}
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	return FLIPGPU_OK;
+}
+
+// rows [j_start, j_start+n_rows) of a grid field (global row numbering, nx elements per row)
+static int rows_copy(FlipSim* f, int field, void* host, int j_start, int n_rows, bool to_device) {
+	FG_CHECK(f && host, FLIPGPU_EINVAL, "null argument");
+	char* base = (char*)grid_field_ptr(f, field);
+	FG_CHECK(base, FLIPGPU_EINVAL, "rows access is for grid fields (got %d)", field);
+	FG_CHECK(j_start >= 0 && n_rows >= 0 && j_start + n_rows <= f->d.f_num_y, FLIPGPU_EINVAL, "rows [%d,%d) outside the grid", j_start, j_start + n_rows);
+	DeviceGuard guard(f->device);
+	size_t off = (size_t)j_start * f->d.f_num_x * 4, bytes = (size_t)n_rows * f->d.f_num_x * 4;
+	if (bytes) {
+		if (to_device) FG_CUDA(cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, f->st));
+		else FG_CUDA(cudaMemcpyAsync(host, base + off, bytes, cudaMemcpyDeviceToHost, f->st));
+	}
+	FG_CUDA(cudaStreamSynchronize(f->st));
+	return FLIPGPU_OK;
+}
+int flip_upload_rows(FlipSim* f, int field, const void* host, int j_start, int n_rows) { return rows_copy(f, field, const_cast<void*>(host), j_start, n_rows, true); }
+int flip_readback_rows(FlipSim* f, int field, void* host, int j_start, int n_rows) { return rows_copy(f, field, host, j_start, n_rows, false); }
 
 int flip_phase_integrate(FlipSim* f, float dt, float gravity) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");

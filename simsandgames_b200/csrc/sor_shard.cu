@@ -11,52 +11,13 @@
 // (tests/test_gpu_multi.py) at 2*iters/K exchanges per solve instead of 2*iters (H=9: 50 instead of 400 for the
 // 200-sweep config), each carrying H rows of the two velocity fields.
 // The lexicographic wavefront is not sharded: its critical path crosses all slabs.
-#include <nccl.h>   // types only: NCCL is bound at run time (see NcclApi) so that single-GPU users never load it
-#include <dlfcn.h>
 #include <algorithm>
 #include <cstdlib>
 #include "common.cuh"
+#define FG_NCCL_SHIM_IMPL
+#include "nccl_shim.cuh"
 
 namespace fg {
-
-// NCCL through dlopen/dlsym.  Linking libnccl at build time would pull the system NCCL into every process that
-// loads this library; a host program that later loads a newer NCCL of the same SONAME (PyTorch bundles one) then
-// fails to resolve its symbols.  Binding lazily means: whichever libnccl.so.2 the process already holds is used,
-// and it is only loaded at all when a sharded object is created.
-struct NcclApi {
-	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-	ncclResult_t (*GroupStart)() = nullptr;
-	ncclResult_t (*GroupEnd)() = nullptr;
-	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-	const char* (*GetErrorString)(ncclResult_t) = nullptr;
-	bool ok = false;
-};
-static NcclApi g_nccl;
-static int load_nccl() {
-	if (g_nccl.ok) return FLIPGPU_OK;
-	void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-	if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-	if (!lib) { fg::set_error("NCCL is not available: %s", dlerror()); return FLIPGPU_ENCCL; }
-#define FG_SYM(field, name) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name)); if (!g_nccl.field) { fg::set_error("NCCL symbol %s missing", name); return FLIPGPU_ENCCL; }
-	FG_SYM(GetUniqueId, "ncclGetUniqueId") FG_SYM(CommInitRank, "ncclCommInitRank") FG_SYM(CommDestroy, "ncclCommDestroy")
-	FG_SYM(GroupStart, "ncclGroupStart") FG_SYM(GroupEnd, "ncclGroupEnd") FG_SYM(Send, "ncclSend") FG_SYM(Recv, "ncclRecv")
-	FG_SYM(GetErrorString, "ncclGetErrorString")
-#undef FG_SYM
-	g_nccl.ok = true;
-	return FLIPGPU_OK;
-}
-
-#define FG_NCCL(call)                                                                          \
-	do {                                                                                       \
-		ncclResult_t r_ = (call);                                                              \
-		if (r_ != ncclSuccess) {                                                               \
-			fg::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, fg::g_nccl.GetErrorString(r_)); \
-			return FLIPGPU_ENCCL;                                                              \
-		}                                                                                      \
-	} while (0)
 
 // one colour of one SOR sweep over local rows [b_lo, b_hi]; `shift` = parity of the global index of local row 0
 template <bool XFAST>
@@ -86,6 +47,15 @@ __global__ void __launch_bounds__(256) sor_rb_rows_kernel(SorGrid g, int colour,
 	g.vel_f[c + 1] = vfp + sfp * pv;
 	g.vel_s[c] = vsc - ssm * pv;
 	g.vel_s[c + nf] = vsp + ssp * pv;
+}
+
+// one colour pass over global rows [lo, hi] of a grid view (used by the sharded FLIP step as well)
+void sor_rb_rows_launch(const SorGrid& g, int colour, int shift, int lo, int hi, float cp, float omega, bool drift, cudaStream_t st) {
+	if (hi < lo) return;
+	dim3 block(64, 4);
+	dim3 grid(cdiv((size_t)(g.nf + 1) / 2 + 1, block.x), cdiv((size_t)(hi - lo + 1), block.y));
+	if (g.x_fast) sor_rb_rows_kernel<true><<<grid, block, 0, st>>>(g, colour, shift, lo, hi, cp, omega, drift);
+	else sor_rb_rows_kernel<false><<<grid, block, 0, st>>>(g, colour, shift, lo, hi, cp, omega, drift);
 }
 
 }  // namespace fg

@@ -12,6 +12,30 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from simsandgames_b200 import parallel  # noqa: E402
 
 
+def run_flip(d, out_prefix, rank, world, local, uid, sg):
+    """this rank's slab of a sharded FLIP run: global scene in, owned particles + own grid rows out"""
+    g = {k: float(d[k]) for k in ("density", "width", "height", "spacing", "radius")}
+    pos, vel = d["pos"].reshape(-1, 2), d["vel"].reshape(-1, 2)
+    sim = sg.FlipFluidSharded(g["density"], g["width"], g["height"], g["spacing"], g["radius"], int(d["capacity"]), rank, world,
+                              unique_id=uid, device=local)
+    for name in ("s", "u", "v"):
+        sim.upload(name, d[name])                      # grid arrays keep the global shape on every rank
+    if float(d["rest"]) != 0.0:
+        sim.particle_rest_density = float(d["rest"])
+    mine = sim.owns(pos)
+    ids = np.flatnonzero(mine).astype(np.int32)
+    sim.upload_particles(pos[mine], vel[mine], ids)
+    kw = dict(dt=float(d["dt"]), gravity=9.81, flip_ratio=0.9, num_pressure_iters=int(d["iters"]), num_particle_iters=2,
+              over_relaxation=1.9, compensate_drift=True, separate_particles=True, obstacle_x=float(d["ox"]), obstacle_y=float(d["oy"]),
+              obstacle_vel_x=0.0, obstacle_vel_y=0.0, obstacle_radius=float(d["orad"]))
+    sim.simulate(**kw, n_steps=int(d["flip_steps"]))
+    p, v, i = sim.readback_particles()
+    np.savez(f"{out_prefix}_rank{rank}.npz", pos=p, vel=v, ids=i, u=sim.readback_own_rows("u"), v=sim.readback_own_rows("v"),
+             p=sim.readback_own_rows("p"), cell_type=sim.readback_own_rows("cell_type"), density=sim.readback_own_rows("particle_density"),
+             rest=np.float32(sim.particle_rest_density), info=np.array(sim.shard_info()))
+    sim.close()
+
+
 def main():
     inputs, out_prefix, backend = sys.argv[1], sys.argv[2], sys.argv[3]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -21,7 +45,7 @@ def main():
         torch.cuda.set_device(local)
     dist.init_process_group(backend, rank=rank, world_size=world)
     d = np.load(inputs)
-    ns, nf = d["vel_fast"].shape
+    ns, nf = d["vel_fast"].shape if "vel_fast" in d.files else (0, 0)
     part = parallel.slab_partition(ns, world)
     if not has_gpu:
         uid = parallel.broadcast_unique_id(lambda: bytes(range(128)))
@@ -37,6 +61,11 @@ def main():
         return
     import simsandgames_b200 as sg
     uid = parallel.broadcast_unique_id()
+    if "flip_steps" in d.files:
+        run_flip(d, out_prefix, rank, world, local, uid, sg)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     sh = sg.ShardedProjection(nf, ns, bool(d["x_fast"]), rank, world, unique_id=uid, device=local)
     assert (sh.j0, sh.j1) == part[rank]
     for name in ("vel_fast", "vel_slow", "p", "s", "density", "cell_type"):

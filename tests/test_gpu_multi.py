@@ -80,3 +80,54 @@ def test_multi_rank_shard_bit_identical_to_one_gpu(tmp_path, make, world):
         assert_bit_equal(got, want[k], f"{world}-rank shard {k}")
     # deep halo: one neighbour exchange every H-1 = 8 colour passes
     assert all(int(pt["counters"][1]) == -(-2 * int(prob["iters"]) // 8) for pt in parts)
+
+
+def _launch(tmp_path, world, inp):
+    port = 29600 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multi_worker.py"), inp, str(tmp_path / "out"), "gloo"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return [np.load(str(tmp_path / f"out_rank{k}.npz")) for k in range(world)]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("start,steps,latch", [(0, 12, True), (40, 10, False)])
+def test_sharded_flip_step_matches_one_gpu(tmp_path, world, start, steps, latch):
+    """The whole FLIP step, slab-sharded over `world` GPUs, against the one-GPU red-black run from the same state.
+    With the rest density given (latch=False) every particle and every grid row is bit-identical; when the latch
+    runs inside the sharded step the cross-rank sum may round differently, so that case is compared to 1e-5."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    o, p, g = co.make_flip_scene("default", oracle_kind="port")
+    o.simulate(**p, n_steps=start)
+    P = o.num_particles
+    rest = 0.0 if latch else float(o.particle_rest_density)
+    one = gpu_like(o, g)
+    if latch:
+        one.particle_rest_density = 0.0
+    from tests.helpers import product_args
+    one.simulate(**product_args(p), n_steps=steps, solver_order=sg.RED_BLACK, update_colors=False)
+    inp = str(tmp_path / "in.npz")
+    np.savez(inp, flip_steps=steps, pos=o.particle_pos[:2 * P], vel=o.particle_vel[:2 * P], s=o.s, u=o.u, v=o.v, rest=rest,
+             capacity=P, dt=p["dt"], iters=50, ox=p["ox"], oy=p["oy"], orad=p["orad"], **{k: g[k] for k in ("density", "width", "height", "spacing", "radius")})
+    parts = _launch(tmp_path, world, inp)
+    ids = np.concatenate([pt["ids"] for pt in parts])
+    assert np.array_equal(np.sort(ids), np.arange(P)), "every particle is owned by exactly one rank"
+    pos = np.empty((P, 2), np.float32); vel = np.empty((P, 2), np.float32)
+    pos[ids] = np.concatenate([pt["pos"] for pt in parts]).reshape(-1, 2)
+    vel[ids] = np.concatenate([pt["vel"] for pt in parts]).reshape(-1, 2)
+    want_pos, want_vel = one.readback("particle_pos").reshape(-1, 2), one.readback("particle_vel").reshape(-1, 2)
+    ny, nx = o.f_num_y, o.f_num_x
+    grids = {k: np.concatenate([pt[k] for pt in parts], axis=0) for k in ("u", "v", "p", "cell_type", "density")}
+    want = {"u": one.readback("u"), "v": one.readback("v"), "p": one.readback("p"), "cell_type": one.readback("cell_type"),
+            "density": one.readback("particle_density")}
+    if latch:
+        assert abs(float(parts[0]["rest"]) - float(one.particle_rest_density)) <= 1e-5 * float(one.particle_rest_density)
+        assert np.abs(pos - want_pos).max() <= 1e-4 and np.abs(vel - want_vel).max() <= 5e-2
+    else:
+        assert_bit_equal(pos, want_pos, f"{world}-rank particle_pos")
+        assert_bit_equal(vel, want_vel, f"{world}-rank particle_vel")
+        for k in grids:
+            assert_bit_equal(grids[k], want[k].reshape(ny, nx), f"{world}-rank {k}")
+    assert all(int(pt["info"][4]) > 0 for pt in parts)   # NCCL exchanges happened
