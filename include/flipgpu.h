@@ -175,14 +175,15 @@ int euler_get_launch_count(EulerSim* sim, long long* launches);
 
 /* ------------------------------------------------------------------ multi-GPU: slab-sharded FLIP step
  * One process per GPU.  The grid is cut into nranks slabs of rows (y); rank r owns rows [j0,j1) and the particles
- * whose cell lies in them.  Every flip_step: ownership by position + ghost refresh (one NCCL neighbour exchange of
- * the particles within `ghost_band_rows` of a boundary), the single-GPU kernels on owned + ghost particles, halo-row
+ * it owns (a bit map over the global_particles caller indices; a particle that leaves the slab is handed to the
+ * neighbour).  Every flip_step: one NCCL neighbour exchange of migrants + ghosts (the owned particles within
+ * `ghost_band_rows` of a boundary; the band follows the fastest particle), the single-GPU kernels on owned + ghost particles, halo-row
  * exchanges of the grid fields after P2G and after the solve, and the red-black projection with the
  * communication-avoiding deep halo (halo_rows rows every halo_rows-1 colour passes).  Positions stay in GLOBAL
  * coordinates and particles carry their global caller index, so with the rest density given the result is
  * bit-identical to the one-GPU FLIP_SOLVER_RED_BLACK run (tests/test_gpu_multi.py).  params->max_particles is the
  * per-rank capacity (owned + ghosts).  Only FLIP_SOLVER_RED_BLACK, update_colors = 0. */
-int flip_create_sharded(const FlipParams* params, int rank, int nranks, const void* unique_id128, FlipSim** out);
+int flip_create_sharded(const FlipParams* params, int global_particles, int rank, int nranks, const void* unique_id128, FlipSim** out);
 int flip_get_shard_info(FlipSim* sim, int* j0, int* j1, int* halo_rows, int* ghost_band_rows, long long* exchanges);
 int flip_upload_particles(FlipSim* sim, const float* pos, const float* vel /* may be NULL = 0 */, const int* global_ids, int n);
 int flip_readback_particles(FlipSim* sim, float* pos, float* vel, int* global_ids, int capacity, int* n_out);

@@ -452,12 +452,13 @@ class FlipFluidSharded(FlipFluidGPU):
     """One rank's slab of a slab-sharded FlipFluid.  Grid arrays keep the global shape (only the rank's
     window rows are current); particles are exchanged as (pos, vel, global id) triples."""
 
-    def __init__(self, density, width, height, spacing, particle_radius, max_local_particles, rank, nranks, unique_id=None, device=-1):
+    def __init__(self, density, width, height, spacing, particle_radius, max_local_particles, global_particles, rank, nranks,
+                 unique_id=None, device=-1):
         self._lib = load_library()
         self._h = C.c_void_p()
         pr = _FlipParams(density, width, height, spacing, particle_radius, max_local_particles, device)
         idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
-        _check(self._lib.flip_create_sharded(C.byref(pr), int(rank), int(nranks), idbuf, C.byref(self._h)), "flip_create_sharded")
+        _check(self._lib.flip_create_sharded(C.byref(pr), int(global_particles), int(rank), int(nranks), idbuf, C.byref(self._h)), "flip_create_sharded")
         self._refresh()
         self.rank, self.nranks = rank, nranks
         self.j0, self.j1, self.halo, self.band, _ = self.shard_info()

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kThreads) k_integrate_bin(Geo g, float2* __res
 __global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int* __restrict__ count, int n, int* __restrict__ tile_sum) {
 	size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
 	int s = 0;
-	if (base + kScanItems <= (size_t)n) {
+	const bool vec = (reinterpret_cast<size_t>(count) & 15) == 0;  // window offsets need not be 16-byte aligned
+	if (vec && base + kScanItems <= (size_t)n) {
 		int4 a = *reinterpret_cast<const int4*>(count + base), b = *reinterpret_cast<const int4*>(count + base + 4);
 		s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
 	} else {
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int* __restri
                                                              const int* __restrict__ tile_off, int* __restrict__ first) {
 	size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
 	int v[kScanItems];
-	if (base + kScanItems <= (size_t)n) {
+	const bool vec = ((reinterpret_cast<size_t>(count) | reinterpret_cast<size_t>(first)) & 15) == 0;
+	if (vec && base + kScanItems <= (size_t)n) {
 		int4 a = *reinterpret_cast<const int4*>(count + base), b = *reinterpret_cast<const int4*>(count + base + 4);
 		v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 	} else {
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const int* __restri
 	}
 	__syncthreads();
 	int off = tile_off[blockIdx.x] + ws[threadIdx.x >> 5] + incl - tot;
-	if (base + kScanItems <= (size_t)n) {
+	if (vec && base + kScanItems <= (size_t)n) {
 		int4 a = make_int4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
 		int4 b = make_int4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
 		*reinterpret_cast<int4*>(first + base) = a;
@@ -643,29 +645,78 @@ __global__ void __launch_bounds__(256) k_set_obstacle(Geo g, float x, float y, f
 struct ShardPack {
 	float2* pos; float2* vel; int* id;
 };
-__global__ void __launch_bounds__(kThreads) k_shard_classify(Geo g, int j0, int j1, int band, int has_down, int has_up,
-                                                             const float2* __restrict__ pos, const float2* __restrict__ vel,
-                                                             const int* __restrict__ id, ShardPack keep, ShardPack down, ShardPack up,
-                                                             int* __restrict__ counters /* [0] keep [1] down [2] up */, int cap_send) {
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
-		float2 p = pos[t];
-		int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
-		if (row < j0 || row >= j1) continue;
-		float2 v = vel[t];
+constexpr int kMigrantFlag = (int)0x80000000u;  // set on the id of a particle that changes owner
+
+// largest |v_y| (+ one gravity kick) over the particles this rank owns, as raw float bits (non-negative floats order like ints)
+__global__ void __launch_bounds__(kThreads) k_shard_vmax(int np, const float2* __restrict__ vel, const int* __restrict__ id,
+                                                         const unsigned* __restrict__ owned_bits, int* __restrict__ vmax_bits) {
+	float m = 0.f;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) {
 		int gid = id[t];
-		int k = atomicAdd(counters + 0, 1);
-		keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
+		if ((owned_bits[gid >> 5] >> (gid & 31)) & 1u) m = fmaxf(m, fabsf(vel[t].y));
+	}
+	int mi = warp_max(__float_as_int(m));
+	if ((threadIdx.x & 31) == 0 && mi > 0) atomicMax(vmax_bits, mi);
+}
+// ghost band in rows: how far a particle can travel in one step (integration + a separation/collision allowance) plus the
+// reach of the bilinear stencil -- every particle that can touch this rank's rows during the step must be present
+__global__ void k_shard_band(const int* __restrict__ vmax_bits, float dt, float gravity, float h, int max_band, int* __restrict__ band) {
+	if (threadIdx.x != 0) return;
+	float v = __int_as_float(*vmax_bits) + fabsf(gravity) * dt;
+	int b = (int)ceilf(v * dt / h) + 4;
+	*band = min(max(b, 6), max_band);
+}
+
+// Step-start bookkeeping.  A particle is OWNED by exactly one rank (bit map over global ids).  For every particle this
+// rank owned last step: still in the slab -> keep (and copy it to a neighbour as a ghost if it lies within `band` rows
+// of that boundary); left the slab -> hand it to the neighbour on that side as a migrant and clear the bit.
+// Everything that was only a ghost last step is dropped.
+__global__ void __launch_bounds__(kThreads) k_shard_classify(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
+                                                             const float2* __restrict__ pos, const float2* __restrict__ vel,
+                                                             const int* __restrict__ id, unsigned* __restrict__ owned_bits, ShardPack keep,
+                                                             ShardPack down, ShardPack up,
+                                                             int* __restrict__ counters /* [0] keep [1] down [2] up */, int cap_send, int exchange) {
+	const int band = exchange ? *band_p : 0;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		int gid = id[t];
+		if (!((owned_bits[gid >> 5] >> (gid & 31)) & 1u)) continue;   // last step's ghost
+		float2 p = pos[t], v = vel[t];
+		int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
+		bool mig_down = exchange && has_down && row < j0, mig_up = exchange && has_up && row >= j1;
+		if (!mig_down && !mig_up) {
+			int k = atomicAdd(counters + 0, 1);
+			keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
+		} else {
+			atomicAnd(owned_bits + (gid >> 5), ~(1u << (gid & 31)));
+		}
+		if (!exchange) continue;
 		if (has_down && row < j0 + band) {
 			int m = atomicAdd(counters + 1, 1);
-			if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = gid; }
+			if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = mig_down ? (gid | kMigrantFlag) : gid; }
 		}
 		if (has_up && row >= j1 - band) {
 			int m = atomicAdd(counters + 2, 1);
-			if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = gid; }
+			if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = mig_up ? (gid | kMigrantFlag) : gid; }
 		}
 	}
 }
-
+// received particles: migrants become owned here
+__global__ void __launch_bounds__(kThreads) k_shard_adopt(int n, int* __restrict__ id, unsigned* __restrict__ owned_bits) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+		int gid = id[t];
+		if (gid & kMigrantFlag) {
+			gid &= ~kMigrantFlag;
+			id[t] = gid;
+			atomicOr(owned_bits + (gid >> 5), 1u << (gid & 31));
+		}
+	}
+}
+__global__ void __launch_bounds__(kThreads) k_shard_set_owned(int n, const int* __restrict__ id, unsigned* __restrict__ owned_bits) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+		int gid = id[t];
+		atomicOr(owned_bits + (gid >> 5), 1u << (gid & 31));
+	}
+}
 
 // rest-density latch across slabs: per-rank (sum, count) over own rows, summed over ranks (flip_fluid.h:321-332)
 __global__ void k_rest_pair(int n_partials, const float* __restrict__ partials, const float* __restrict__ rest, float* __restrict__ pair) {
@@ -715,7 +766,9 @@ struct FlipSim {
 	float2 *send_pos[2] = {nullptr, nullptr}, *send_vel[2] = {nullptr, nullptr};
 	int* send_id[2] = {nullptr, nullptr};
 	int cap_send = 0;
-	int* d_counters = nullptr;   // [0] keep [1] down [2] up [3] from-down [4] from-up
+	int* d_counters = nullptr;   // [0] keep [1] down [2] up [3] from-down [4] from-up [5] vmax bits [6] ghost band (rows)
+	unsigned* owned_bits = nullptr;  // bit per GLOBAL particle id: this rank owns it
+	int global_particles = 0;
 	int* h_counters = nullptr;   // pinned mirror
 	int n_owned = 0;
 	long long exchanges = 0;
@@ -983,19 +1036,24 @@ int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows)
 	return FLIPGPU_OK;
 }
 
-// keep what this rank owns, refresh the ghosts from both neighbours
-int shard_exchange_particles(FlipSim* f) {
+// keep what this rank owns, hand over what left the slab, refresh the ghosts from both neighbours
+int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 	Geo g = geo(f);
 	const int c = f->cur, n = 1 - c;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
+	// ghost band for this step from the fastest owned particle anywhere (device-side: no host round trip)
+	if (g.np > 0) { k_shard_vmax<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->vel[c], f->orig[c], f->owned_bits, f->d_counters + 5); f->lc.n++; }
+	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 5, f->d_counters + 5, 1, ncclInt, ncclMax, f->comm, f->st));
+	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 5, dt, gravity, f->d.h, std::max(f->j1 - f->j0 - 1, 6), f->d_counters + 6);
+	f->lc.n++;
 	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
 	if (g.np > 0) {
-		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, f->band, has_down, has_up, f->pos[c], f->vel[c], f->orig[c], keep,
-		                                                    down, up, f->d_counters, f->cap_send);
+		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, f->d_counters + 6, has_down, has_up, f->pos[c], f->vel[c], f->orig[c],
+		                                                    f->owned_bits, keep, down, up, f->d_counters, f->cap_send, 1);
 		f->lc.n++;
 	}
-	// tell each neighbour how many ghosts are coming (device-to-device ints), then read all five counters once
+	// tell each neighbour how many particles are coming (device-to-device ints), then read the counters once
 	if (f->nranks > 1) {
 		FG_NCCL(g_nccl.GroupStart());
 		if (has_down) {
@@ -1011,8 +1069,9 @@ int shard_exchange_particles(FlipSim* f) {
 	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	const int n_keep = f->h_counters[0], n_down = f->h_counters[1], n_up = f->h_counters[2], from_down = f->h_counters[3], from_up = f->h_counters[4];
-	FG_CHECK(n_down <= f->cap_send && n_up <= f->cap_send, FLIPGPU_ESTATE, "shard: %d/%d ghost particles exceed the send capacity %d", n_down, n_up, f->cap_send);
-	FG_CHECK((long long)n_keep + from_down + from_up <= f->d.max_particles, FLIPGPU_ESTATE, "shard: %d owned + %d + %d ghosts exceed max_particles %d",
+	f->band = f->h_counters[6];
+	FG_CHECK(n_down <= f->cap_send && n_up <= f->cap_send, FLIPGPU_ESTATE, "shard: %d/%d boundary particles exceed the send capacity %d", n_down, n_up, f->cap_send);
+	FG_CHECK((long long)n_keep + from_down + from_up <= f->d.max_particles, FLIPGPU_ESTATE, "shard: %d owned + %d + %d received exceed max_particles %d",
 	         n_keep, from_down, from_up, f->d.max_particles);
 	if (f->nranks > 1) {
 		FG_NCCL(g_nccl.GroupStart());
@@ -1036,7 +1095,13 @@ int shard_exchange_particles(FlipSim* f) {
 		}
 		FG_NCCL(g_nccl.GroupEnd());
 		f->exchanges++;
+		const int n_recv = from_down + from_up;
+		if (n_recv > 0) {
+			k_shard_adopt<<<wave_grid(n_recv, kThreads), kThreads, 0, f->st>>>(n_recv, f->orig[n] + n_keep, f->owned_bits);
+			f->lc.n++;
+		}
 	}
+	FG_CUDA(cudaGetLastError());
 	f->cur = n;
 	f->n_owned = n_keep;
 	f->d.num_particles = n_keep + from_down + from_up;
@@ -1070,8 +1135,10 @@ int shard_step(FlipSim* f, const FlipStepParams* sp) {
 	FG_CHECK(sp->solver_order == FLIP_SOLVER_RED_BLACK, FLIPGPU_EINVAL, "a sharded simulation runs the red-black order (the lexicographic wavefront does not shard)");
 	FG_CHECK(!sp->update_colors, FLIPGPU_EINVAL, "render-state colours are not kept in sharded mode");
 	const float cp = f->d.density * f->d.h / sp->dt;
+	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity));              // migrants change owner, ghosts are refreshed
+	// (the exchange synchronised the stream, so the previous step -- and its copy of the rest density -- is complete on
+	// every rank: all ranks take the same branch below and issue the same NCCL calls)
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
-	FG_TRY(shard_exchange_particles(f));                                   // ownership by position + ghost refresh
 	FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));         // owned + ghosts
 	if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, false));
 	FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
@@ -1232,6 +1299,7 @@ int flip_destroy(FlipSim* f) {
 	if (f->comm) g_nccl.CommDestroy(f->comm);
 	for (int k = 0; k < 2; k++) { cudaFree(f->send_pos[k]); cudaFree(f->send_vel[k]); cudaFree(f->send_id[k]); }
 	cudaFree(f->d_counters);
+	cudaFree(f->owned_bits);
 	if (f->h_counters) cudaFreeHost(f->h_counters);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
 	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
@@ -1415,8 +1483,8 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 
 
 // ------------------------------------------------------------------ slab-sharded FLIP
-int flip_create_sharded(const FlipParams* pr, int rank, int nranks, const void* unique_id128, FlipSim** out) {
-	FG_CHECK(pr && out && nranks >= 1 && rank >= 0 && rank < nranks, FLIPGPU_EINVAL, "flip_create_sharded: bad argument");
+int flip_create_sharded(const FlipParams* pr, int global_particles, int rank, int nranks, const void* unique_id128, FlipSim** out) {
+	FG_CHECK(pr && out && nranks >= 1 && rank >= 0 && rank < nranks && global_particles >= 0, FLIPGPU_EINVAL, "flip_create_sharded: bad argument");
 	FG_CHECK(nranks == 1 || unique_id128, FLIPGPU_EINVAL, "flip_create_sharded: a NCCL unique id is required for %d ranks", nranks);
 	FlipSim* f = nullptr;
 	FG_TRY(flip_create(pr, &f));
@@ -1433,7 +1501,10 @@ int flip_create_sharded(const FlipParams* pr, int rank, int nranks, const void* 
 	f->gy0 = std::max(f->j0 - f->halo, 0); f->gy1 = std::min(f->j1 + f->halo, ny);
 	f->hy0 = std::max((int)((float)f->gy0 * f->d.h * f->d.p_inv_spacing) - 1, 0);
 	f->hy1 = std::min((int)((float)f->gy1 * f->d.h * f->d.p_inv_spacing) + 2, f->d.p_num_y);
-	f->cap_send = std::max(f->d.max_particles / 3, 1024);
+	f->cap_send = std::max(f->d.max_particles / 2, 1024);
+	f->global_particles = global_particles;
+	FG_CUDA(cudaMalloc(&f->owned_bits, ((size_t)global_particles / 32 + 1) * 4));
+	FG_CUDA(cudaMemset(f->owned_bits, 0, ((size_t)global_particles / 32 + 1) * 4));
 	for (int k = 0; k < 2; k++) {
 		FG_CUDA(cudaMalloc(&f->send_pos[k], (size_t)f->cap_send * sizeof(float2)));
 		FG_CUDA(cudaMalloc(&f->send_vel[k], (size_t)f->cap_send * sizeof(float2)));
@@ -1473,6 +1544,9 @@ int flip_upload_particles(FlipSim* f, const float* pos, const float* vel, const 
 		else FG_CUDA(cudaMemsetAsync(f->vel[c], 0, (size_t)n * sizeof(float2), f->st));
 		FG_CUDA(cudaMemcpyAsync(f->orig[c], ids, (size_t)n * 4, cudaMemcpyHostToDevice, f->st));
 	}
+	FG_CUDA(cudaMemsetAsync(f->owned_bits, 0, ((size_t)f->global_particles / 32 + 1) * 4, f->st));
+	if (n) { k_shard_set_owned<<<wave_grid(n, kThreads), kThreads, 0, f->st>>>(n, f->orig[c], f->owned_bits); f->lc.n++; }
+	FG_CUDA(cudaGetLastError());
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	f->d.num_particles = n; f->n_owned = n; f->bins_valid = false; f->identity = false;
 	return FLIPGPU_OK;
@@ -1488,7 +1562,8 @@ int flip_readback_particles(FlipSim* f, float* pos, float* vel, int* ids, int ca
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
 	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, none{nullptr, nullptr, nullptr};
 	if (g.np > 0) {
-		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, 0, 0, 0, f->pos[c], f->vel[c], f->orig[c], keep, none, none, f->d_counters, 0);
+		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, nullptr, 0, 0, f->pos[c], f->vel[c], f->orig[c], f->owned_bits, keep, none, none,
+		                                                    f->d_counters, 0, 0);
 		f->lc.n++;
 	}
 	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
