@@ -175,9 +175,10 @@ int euler_get_launch_count(EulerSim* sim, long long* launches);
 
 /* ------------------------------------------------------------------ multi-GPU: slab-sharded FLIP step
  * One process per GPU.  The grid is cut into nranks slabs of rows (y); rank r owns rows [j0,j1) and the particles
- * it owns (a bit map over the global_particles caller indices; a particle that leaves the slab is handed to the
- * neighbour).  Every flip_step: one NCCL neighbour exchange of migrants + ghosts (the owned particles within
- * `ghost_band_rows` of a boundary; the band follows the fastest particle), the single-GPU kernels on owned + ghost particles, halo-row
+ * whose cell lies in them (ownership by position; global_particles = the number of caller indices in use).
+ * Every flip_step: one NCCL neighbour exchange of ghosts (the owned particles within `ghost_band_rows` of a
+ * boundary; the band follows the fastest particle, so a particle that crosses a boundary is always already present
+ * on its new owner), the single-GPU kernels on owned + ghost particles, halo-row
  * exchanges of the grid fields after P2G and after the solve, and the red-black projection with the
  * communication-avoiding deep halo (halo_rows rows every halo_rows-1 colour passes).  Positions stay in GLOBAL
  * coordinates and particles carry their global caller index, so with the rest density given the result is

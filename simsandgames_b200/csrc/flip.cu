@@ -645,16 +645,10 @@ __global__ void __launch_bounds__(256) k_set_obstacle(Geo g, float x, float y, f
 struct ShardPack {
 	float2* pos; float2* vel; int* id;
 };
-constexpr int kMigrantFlag = (int)0x80000000u;  // set on the id of a particle that changes owner
-
-// largest |v_y| (+ one gravity kick) over the particles this rank owns, as raw float bits (non-negative floats order like ints)
-__global__ void __launch_bounds__(kThreads) k_shard_vmax(int np, const float2* __restrict__ vel, const int* __restrict__ id,
-                                                         const unsigned* __restrict__ owned_bits, int* __restrict__ vmax_bits) {
+// largest |v_y| over the local particles, as raw float bits (non-negative floats order like ints)
+__global__ void __launch_bounds__(kThreads) k_shard_vmax(int np, const float2* __restrict__ vel, int* __restrict__ vmax_bits) {
 	float m = 0.f;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) {
-		int gid = id[t];
-		if ((owned_bits[gid >> 5] >> (gid & 31)) & 1u) m = fmaxf(m, fabsf(vel[t].y));
-	}
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(vel[t].y));
 	int mi = warp_max(__float_as_int(m));
 	if ((threadIdx.x & 31) == 0 && mi > 0) atomicMax(vmax_bits, mi);
 }
@@ -667,54 +661,33 @@ __global__ void k_shard_band(const int* __restrict__ vmax_bits, float dt, float 
 	*band = min(max(b, 6), max_band);
 }
 
-// Step-start bookkeeping.  A particle is OWNED by exactly one rank (bit map over global ids).  For every particle this
-// rank owned last step: still in the slab -> keep (and copy it to a neighbour as a ghost if it lies within `band` rows
-// of that boundary); left the slab -> hand it to the neighbour on that side as a migrant and clear the bit.
-// Everything that was only a ghost last step is dropped.
+// Step-start bookkeeping.  Ownership is by position: a rank owns the particles whose cell row lies in its slab.  Out of
+// every copy it simulated last step (its own particles and the ghosts) a rank keeps exactly those; a particle that
+// crossed the boundary was a ghost on its new owner, whose copy -- integrated, separated and G2P'd inside that rank's
+// valid rows -- is the one that survives.  (The band below is wide enough that every such particle WAS a ghost there.)
+// Kept particles within `band` rows of a boundary are copied to that neighbour as this step's ghosts.
 __global__ void __launch_bounds__(kThreads) k_shard_classify(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
                                                              const float2* __restrict__ pos, const float2* __restrict__ vel,
-                                                             const int* __restrict__ id, unsigned* __restrict__ owned_bits, ShardPack keep,
-                                                             ShardPack down, ShardPack up,
+                                                             const int* __restrict__ id, ShardPack keep, ShardPack down, ShardPack up,
                                                              int* __restrict__ counters /* [0] keep [1] down [2] up */, int cap_send, int exchange) {
 	const int band = exchange ? *band_p : 0;
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
-		int gid = id[t];
-		if (!((owned_bits[gid >> 5] >> (gid & 31)) & 1u)) continue;   // last step's ghost
-		float2 p = pos[t], v = vel[t];
+		float2 p = pos[t];
 		int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
-		bool mig_down = exchange && has_down && row < j0, mig_up = exchange && has_up && row >= j1;
-		if (!mig_down && !mig_up) {
-			int k = atomicAdd(counters + 0, 1);
-			keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
-		} else {
-			atomicAnd(owned_bits + (gid >> 5), ~(1u << (gid & 31)));
-		}
+		if (row < j0 || row >= j1) continue;
+		float2 v = vel[t];
+		int gid = id[t];
+		int k = atomicAdd(counters + 0, 1);
+		keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
 		if (!exchange) continue;
 		if (has_down && row < j0 + band) {
 			int m = atomicAdd(counters + 1, 1);
-			if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = mig_down ? (gid | kMigrantFlag) : gid; }
+			if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = gid; }
 		}
 		if (has_up && row >= j1 - band) {
 			int m = atomicAdd(counters + 2, 1);
-			if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = mig_up ? (gid | kMigrantFlag) : gid; }
+			if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = gid; }
 		}
-	}
-}
-// received particles: migrants become owned here
-__global__ void __launch_bounds__(kThreads) k_shard_adopt(int n, int* __restrict__ id, unsigned* __restrict__ owned_bits) {
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-		int gid = id[t];
-		if (gid & kMigrantFlag) {
-			gid &= ~kMigrantFlag;
-			id[t] = gid;
-			atomicOr(owned_bits + (gid >> 5), 1u << (gid & 31));
-		}
-	}
-}
-__global__ void __launch_bounds__(kThreads) k_shard_set_owned(int n, const int* __restrict__ id, unsigned* __restrict__ owned_bits) {
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-		int gid = id[t];
-		atomicOr(owned_bits + (gid >> 5), 1u << (gid & 31));
 	}
 }
 
@@ -767,7 +740,6 @@ struct FlipSim {
 	int* send_id[2] = {nullptr, nullptr};
 	int cap_send = 0;
 	int* d_counters = nullptr;   // [0] keep [1] down [2] up [3] from-down [4] from-up [5] vmax bits [6] ghost band (rows)
-	unsigned* owned_bits = nullptr;  // bit per GLOBAL particle id: this rank owns it
 	int global_particles = 0;
 	int* h_counters = nullptr;   // pinned mirror
 	int n_owned = 0;
@@ -1036,21 +1008,21 @@ int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows)
 	return FLIPGPU_OK;
 }
 
-// keep what this rank owns, hand over what left the slab, refresh the ghosts from both neighbours
+// keep what this rank owns (by position), refresh the ghosts from both neighbours
 int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 	Geo g = geo(f);
 	const int c = f->cur, n = 1 - c;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
 	// ghost band for this step from the fastest owned particle anywhere (device-side: no host round trip)
-	if (g.np > 0) { k_shard_vmax<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->vel[c], f->orig[c], f->owned_bits, f->d_counters + 5); f->lc.n++; }
+	if (g.np > 0) { k_shard_vmax<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->vel[c], f->d_counters + 5); f->lc.n++; }
 	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 5, f->d_counters + 5, 1, ncclInt, ncclMax, f->comm, f->st));
 	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 5, dt, gravity, f->d.h, std::max(f->j1 - f->j0 - 1, 6), f->d_counters + 6);
 	f->lc.n++;
 	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
 	if (g.np > 0) {
 		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, f->d_counters + 6, has_down, has_up, f->pos[c], f->vel[c], f->orig[c],
-		                                                    f->owned_bits, keep, down, up, f->d_counters, f->cap_send, 1);
+		                                                    keep, down, up, f->d_counters, f->cap_send, 1);
 		f->lc.n++;
 	}
 	// tell each neighbour how many particles are coming (device-to-device ints), then read the counters once
@@ -1095,11 +1067,6 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 		}
 		FG_NCCL(g_nccl.GroupEnd());
 		f->exchanges++;
-		const int n_recv = from_down + from_up;
-		if (n_recv > 0) {
-			k_shard_adopt<<<wave_grid(n_recv, kThreads), kThreads, 0, f->st>>>(n_recv, f->orig[n] + n_keep, f->owned_bits);
-			f->lc.n++;
-		}
 	}
 	FG_CUDA(cudaGetLastError());
 	f->cur = n;
@@ -1299,7 +1266,6 @@ int flip_destroy(FlipSim* f) {
 	if (f->comm) g_nccl.CommDestroy(f->comm);
 	for (int k = 0; k < 2; k++) { cudaFree(f->send_pos[k]); cudaFree(f->send_vel[k]); cudaFree(f->send_id[k]); }
 	cudaFree(f->d_counters);
-	cudaFree(f->owned_bits);
 	if (f->h_counters) cudaFreeHost(f->h_counters);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
 	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
@@ -1503,8 +1469,6 @@ int flip_create_sharded(const FlipParams* pr, int global_particles, int rank, in
 	f->hy1 = std::min((int)((float)f->gy1 * f->d.h * f->d.p_inv_spacing) + 2, f->d.p_num_y);
 	f->cap_send = std::max(f->d.max_particles / 2, 1024);
 	f->global_particles = global_particles;
-	FG_CUDA(cudaMalloc(&f->owned_bits, ((size_t)global_particles / 32 + 1) * 4));
-	FG_CUDA(cudaMemset(f->owned_bits, 0, ((size_t)global_particles / 32 + 1) * 4));
 	for (int k = 0; k < 2; k++) {
 		FG_CUDA(cudaMalloc(&f->send_pos[k], (size_t)f->cap_send * sizeof(float2)));
 		FG_CUDA(cudaMalloc(&f->send_vel[k], (size_t)f->cap_send * sizeof(float2)));
@@ -1544,9 +1508,6 @@ int flip_upload_particles(FlipSim* f, const float* pos, const float* vel, const 
 		else FG_CUDA(cudaMemsetAsync(f->vel[c], 0, (size_t)n * sizeof(float2), f->st));
 		FG_CUDA(cudaMemcpyAsync(f->orig[c], ids, (size_t)n * 4, cudaMemcpyHostToDevice, f->st));
 	}
-	FG_CUDA(cudaMemsetAsync(f->owned_bits, 0, ((size_t)f->global_particles / 32 + 1) * 4, f->st));
-	if (n) { k_shard_set_owned<<<wave_grid(n, kThreads), kThreads, 0, f->st>>>(n, f->orig[c], f->owned_bits); f->lc.n++; }
-	FG_CUDA(cudaGetLastError());
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	f->d.num_particles = n; f->n_owned = n; f->bins_valid = false; f->identity = false;
 	return FLIPGPU_OK;
@@ -1562,7 +1523,7 @@ int flip_readback_particles(FlipSim* f, float* pos, float* vel, int* ids, int ca
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
 	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, none{nullptr, nullptr, nullptr};
 	if (g.np > 0) {
-		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, nullptr, 0, 0, f->pos[c], f->vel[c], f->orig[c], f->owned_bits, keep, none, none,
+		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, nullptr, 0, 0, f->pos[c], f->vel[c], f->orig[c], keep, none, none,
 		                                                    f->d_counters, 0, 0);
 		f->lc.n++;
 	}
