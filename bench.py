@@ -197,6 +197,91 @@ def eulerian_bench(local_rank, x=2048, y=2048, iters=100, steps=10):
     return out
 
 
+def sharded_flip_bench(args, rank, world, local_rank):
+    """N>1 headline: ONE slab-sharded FlipFluid over `world` GPUs (SURVEY 8d weak-scaling series): `world` dam-break tanks of
+    BASELINE configs[2] stacked along y (the partition axis) and separated by solid rows, each rank owning one tank's rows.
+    Every step runs the real exchanges: ghost particles, halo rows after P2G and after the solve, deep-halo red-black sweeps."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import simsandgames_b200 as sg
+    from simsandgames_b200 import parallel, scenes
+    f32 = np.float32
+    N = args.grid
+    sp = f32(3) / f32(N)
+    width = float((f32(N) - f32(.5)) * sp)
+    height = float((f32(N * world) - f32(.5)) * sp)
+    radius = float(f32(.19) * sp)
+    dt = float((f32(1) / f32(60)) * (f32(100) / f32(N)))
+    tank_h = float((f32(N) - f32(.5)) * sp)
+    pos, _, P0 = scenes.tank_particles(width, tank_h, float(sp), radius, want_s=False)
+    uid = parallel.broadcast_unique_id()
+    sim = sg.FlipFluidSharded(1000.0, width, height, float(sp), radius, int(P0 * 1.3), P0 * world, rank, world, unique_id=uid, device=local_rank)
+    assert (sim.f_num_x, sim.f_num_y) == (N, N * world) and (sim.j0, sim.j1) == (rank * N, (rank + 1) * N)
+    pos = pos.reshape(-1, 2)
+    pos[:, 1] += f32(rank * N) * f32(sim.h)                      # this rank's tank sits in its own rows
+    h_pos = torch.from_numpy(pos.reshape(-1)).pin_memory()
+    h_ids = torch.arange(rank * P0, (rank + 1) * P0, dtype=torch.int32).pin_memory()
+    w0, w1 = max(sim.j0 - sim.halo, 0), min(sim.j1 + sim.halo, sim.f_num_y)
+    jj = np.arange(w0, w1)[:, None] % N
+    s = np.ones((w1 - w0, N), np.float32)
+    s[:, 0] = 0; s[:, -1] = 0
+    s[(jj == 0)[:, 0] | (jj == N - 1)[:, 0]] = 0                 # floor and ceiling of every tank
+    h_s = torch.from_numpy(s.reshape(-1)).pin_memory()
+    h_zero = torch.zeros((w1 - w0) * N, dtype=torch.float32).pin_memory()
+    kw = dict(dt=dt, gravity=9.81, flip_ratio=0.9, num_pressure_iters=50, num_particle_iters=2, over_relaxation=1.9, compensate_drift=True,
+              separate_particles=True, obstacle_x=0.0, obstacle_y=0.0, obstacle_vel_x=0.0, obstacle_vel_y=0.0, obstacle_radius=0.0)
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
+
+    def reseed():
+        for name in ("u", "v", "prev_u", "prev_v", "p", "particle_density"):
+            sim.upload_rows_from(name, h_zero.data_ptr(), w0, w1 - w0)
+        sim.upload_rows_from("s", h_s.data_ptr(), w0, w1 - w0)
+        sim.particle_rest_density = 0.0
+        sim.upload_particles_from(h_pos.data_ptr(), h_ids.data_ptr(), P0)
+        sim.simulate(**kw, n_steps=args.warmup)
+
+    SEG = 8   # red-black at 50 sweeps leaves the regime the reference stays in a little earlier than the lexicographic order
+    ms, done = 0.0, 0
+    launches = 0
+    while done < args.steps:
+        n = min(SEG, args.steps - done)
+        reseed(); barrier()
+        l0 = sim.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.simulate(**kw, n_steps=n)
+        e1.record(stream)
+        barrier()
+        ms += e0.elapsed_time(e1); launches += sim.launch_count - l0; done += n
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    # end to end with host buffers: per step the caller's grid write (s rows) goes H2D, the owned particle positions come back D2H
+    e2e_steps = max(3, min(args.steps, 6))
+    h_out = torch.empty(2 * int(P0 * 1.3), dtype=torch.float32).pin_memory()
+    reseed(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.upload_rows_from("s", h_s.data_ptr(), w0, w1 - w0)
+        sim.simulate(**kw, n_steps=1)
+        n_own = sim.readback_owned_pos_into(h_out.data_ptr(), int(P0 * 1.3))
+    sim.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall * 1e3], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    cnt = torch.tensor([n_own], dtype=torch.int64, device="cuda"); dist.all_reduce(cnt)
+    assert int(cnt.item()) == P0 * world, "particles lost or duplicated across ranks"
+    j0, j1, halo, band, exchanges = sim.shard_info()
+    info = dict(ms_total=ms_max, P_global=P0 * world, P_per_gpu=P0, launches=launches, e2e_ms=e2e_ms, e2e_steps=e2e_steps,
+                h2d=int(h_s.numel() * 4), d2h=int(n_own * 8), halo_rows=halo, ghost_band_rows=band, nccl_exchanges=exchanges,
+                grid=[N, N * world])
+    sim.close()
+    return info
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -230,6 +315,40 @@ def product_arm(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1:
+        info = sharded_flip_bench(args, rank, world, local_rank)
+        shard = sharded_solver_bench(rank, world, local_rank)
+        if rank == 0:
+            peak, peak_src = peaks()
+            N = args.grid
+            s_per_step = info["ms_total"] * 1e-3 / args.steps
+            step_bytes = 140.0 * info["P_global"] + (96.0 + 36.0 * 50) * float(N) * N * world
+            line = {
+                "metric": METRIC, "value": info["P_global"] / s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": info["ms_total"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{world} x ({WORKLOAD}) as ONE slab-sharded FlipFluid: the tanks are stacked along y and separated by solid rows (SURVEY 8d weak-scaling series)",
+                           "grid": info["grid"], "particles_per_gpu": info["P_per_gpu"], "pressure_iters": 50, "separation_sweeps": 2,
+                           "solver_order": "red_black (the sharded order; the 1-GPU headline uses the lexicographic wavefront, which does not shard)",
+                           "parallelism": f"y-slabs over {world} GPUs, one process per GPU; per step: 1 ghost-particle exchange, halo rows after P2G and after the solve, "
+                                          f"{info['halo_rows']}-row deep-halo red-black sweeps (1 exchange per {info['halo_rows'] - 1} colour passes), all NCCL send/recv over NVLink",
+                           "halo_rows": info["halo_rows"], "ghost_band_rows_last_step": info["ghost_band_rows"], "nccl_exchanges_total": info["nccl_exchanges"],
+                           "reseed": f"state re-seeded (untimed, +{args.warmup} warm-up steps) every 8 timed steps (profiles/r1_stability.md)",
+                           "l2": "working set ~4.7 GB per GPU per step >> 126 MB L2", "colours": "off",
+                           "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
+                "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "sampled at N=1 only"},
+                "e2e": {"value": info["P_global"] * info["e2e_steps"] / (info["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": info["h2d"],
+                        "d2h_bytes_per_step": info["d2h"], "steps": info["e2e_steps"],
+                        "what": "per rank and step: flip_upload_rows(s) H2D + sharded flip_step + flip_readback_particles(owned positions) D2H, pinned host buffers, host wall clock, max over ranks"},
+                "gpu_launches": int(info["launches"]),
+                "roofline": {"bound": "hbm", "kernel": "whole sharded step (per GPU)", "achieved": step_bytes / world / s_per_step / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": step_bytes / world / s_per_step / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "formula": "140*P + (96+36*iters)*C per GPU (SURVEY 8d)"},
+                "sharded_solver": shard,
+            }
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
     N = args.grid
     sim, kw, geo = sg.scenes.make_flip_tank("synthetic", N=N, device=local_rank)
     P, nx, ny = sim.num_particles, sim.f_num_x, sim.f_num_y

@@ -494,6 +494,22 @@ class FlipFluidSharded(FlipFluidGPU):
         k = n.value
         return pos[:2 * k].copy(), vel[:2 * k].copy(), ids[:k].copy()
 
+    def readback_owned_pos_into(self, ptr, capacity):
+        """owned particle positions -> raw (pinned) host pointer; returns how many particles"""
+        n = C.c_int()
+        _check(self._lib.flip_readback_particles(self._h, C.cast(C.c_void_p(ptr), C.POINTER(C.c_float)), None, None, int(capacity), C.byref(n)),
+               "flip_readback_particles")
+        return n.value
+
+    def upload_particles_from(self, pos_ptr, ids_ptr, n):
+        _check(self._lib.flip_upload_particles(self._h, C.cast(C.c_void_p(pos_ptr), C.POINTER(C.c_float)), None,
+                                               C.cast(C.c_void_p(ids_ptr), C.POINTER(C.c_int)), int(n)), "flip_upload_particles")
+        self._num_particles = int(n)
+
+    def upload_rows_from(self, name, ptr, j_start, n_rows):
+        fid, _ = FLIP_FIELDS[name]
+        _check(self._lib.flip_upload_rows(self._h, fid, C.c_void_p(ptr), int(j_start), int(n_rows)), f"flip_upload_rows({name})")
+
     def upload_rows(self, name, rows, j_start):
         fid, dt = FLIP_FIELDS[name]
         a = np.ascontiguousarray(rows, dtype=dt).reshape(-1, self.f_num_x)
