@@ -316,6 +316,7 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true> : (const void*)sor_gs_tiled_kernel<true, false>)
 	                          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true> : (const void*)sor_gs_tiled_kernel<false, false>);
 	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * w->kc, 0));
+	if (const char* e = getenv("FLIPGPU_TILE_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
 	int blocks = std::min(w->n_tiles, std::max(1, per_sm) * w->sms);
 	void* args[] = {&A};
 	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, 0, st));
