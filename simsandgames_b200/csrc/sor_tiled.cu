@@ -53,7 +53,7 @@ __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
 }
 
 template <bool XFAST, bool DRIFT>
-__global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledArgs A) {
+__global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_tiled_kernel(TiledArgs A) {
 	__shared__ float s_vf[kBoxW * kBoxW];
 	__shared__ float s_vs[kBoxW * kBoxW];
 	__shared__ float s_p[kBoxW * kBoxW];
@@ -92,20 +92,34 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 		}
 		const int F0 = 1 + I * kTile, S0 = 1 + J * kTile;
 		const int FB = F0 - A.kc + 1, SB = S0 - A.kc + 1;  // box origin (cells FB..FB+kBoxW-1)
-		// ---- stage the box (L2-coherent loads: the producers are other CTAs of this launch)
-		for (int e = tid; e < kBoxW * kBoxW; e += nthreads) {
-			int lf = e % kBoxW, ls = e / kBoxW;
-			int F = FB + lf, S = SB + ls;
-			float vf = 0.f, vs = 0.f, pp = 0.f, dr = 0.f;
-			unsigned char cd = 0;
-			if (F >= 0 && F < nf && S >= 0 && S < ns) {
-				size_t c = (size_t)F + (size_t)nf * S;
-				vf = __ldcg(A.vel_f + c); vs = __ldcg(A.vel_s + c); pp = __ldcg(A.p + c);
-				cd = A.code[c];
-				if (DRIFT) dr = A.drift[c];
+		// ---- stage the box (L2-coherent loads: the producers are other CTAs of this launch).  All loads of a thread are
+		// issued before any is consumed, so the box costs one L2 round trip instead of one per element: the tile sits on
+		// the critical path of the wavefront and its fixed costs are paid once per wave.
+		{
+			constexpr int kRounds = (kBoxW * kBoxW + kTile * kMaxChunk - 1) / (kTile * kMaxChunk);
+			float r_vf[kRounds], r_vs[kRounds], r_p[kRounds], r_dr[kRounds];
+			unsigned char r_cd[kRounds];
+#pragma unroll
+			for (int r = 0; r < kRounds; r++) {
+				int e = tid + r * nthreads;
+				int lf = e % kBoxW, ls = e / kBoxW;
+				int F = FB + lf, S = SB + ls;
+				r_vf[r] = 0.f; r_vs[r] = 0.f; r_p[r] = 0.f; r_dr[r] = 0.f; r_cd[r] = 0;
+				if (e < kBoxW * kBoxW && F >= 0 && F < nf && S >= 0 && S < ns) {
+					size_t c = (size_t)F + (size_t)nf * S;
+					r_vf[r] = __ldcg(A.vel_f + c); r_vs[r] = __ldcg(A.vel_s + c); r_p[r] = __ldcg(A.p + c);
+					r_cd[r] = A.code[c];
+					if (DRIFT) r_dr[r] = A.drift[c];
+				}
 			}
-			s_vf[e] = vf; s_vs[e] = vs; s_p[e] = pp; s_code[e] = cd;
-			if (DRIFT) s_dr[e] = dr;
+#pragma unroll
+			for (int r = 0; r < kRounds; r++) {
+				int e = tid + r * nthreads;
+				if (e < kBoxW * kBoxW) {
+					s_vf[e] = r_vf[r]; s_vs[e] = r_vs[r]; s_p[e] = r_p[r]; s_code[e] = r_cd[r];
+					if (DRIFT) s_dr[e] = r_dr[r];
+				}
+			}
 		}
 		__syncthreads();
 		long long c2 = clock64();
@@ -119,14 +133,16 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 				for (int k = threadIdx.y; k < kq; k += blockDim.y) {
 					// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
 					int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
+					// every operand is fetched before the activity test: one shared-memory round trip per step instead of two
 					unsigned cd = s_code[e];
+					float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[e + kBoxW], pp = s_p[e];
+					float dr = DRIFT ? s_dr[e] : 0.f;
 					if (!(cd & 1u)) continue;
-					float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[e + kBoxW];
 					float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
-					if (DRIFT) div -= s_dr[e];   // the stored term is max(0, density-rest): subtracting 0 is exact
+					if (DRIFT) div -= dr;        // the stored term is max(0, density-rest): subtracting 0 is exact
 					if (cd == 31u) {             // all four neighbours open: s_sum = 4 and x/4 == x*0.25 exactly
 						float pv = (-div * 0.25f) * A.omega;
-						s_p[e] += A.cp * pv;
+						s_p[e] = pp + A.cp * pv;
 						s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[e + kBoxW] = vsp + pv;
 					} else {
 						float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
@@ -134,7 +150,7 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 						float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
 						float pv = -div / ssum;
 						pv *= A.omega;
-						s_p[e] += A.cp * pv;
+						s_p[e] = pp + A.cp * pv;
 						s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
 						s_vs[e] = vsc - ssm * pv; s_vs[e + kBoxW] = vsp + ssp * pv;
 					}
@@ -162,9 +178,10 @@ __global__ void __launch_bounds__(kTile * kMaxChunk) sor_gs_tiled_kernel(TiledAr
 			if (own || from_f) __stcg(A.vel_f + c, s_vf[e]);
 			if (own || from_s) __stcg(A.vel_s + c, s_vs[e]);
 		}
-		__threadfence();
+		// release: every thread has stored, bar.sync, then ONE thread fences (cumulative at gpu scope) and raises the flag
 		__syncthreads();
 		if (tid == 0) {
+			__threadfence();
 			*((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
 			if (A.prof) {
 				long long c4 = clock64();
@@ -311,11 +328,11 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
 	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega; A.prof = w->prof;
 	A.act = w->act; A.na = w->na; A.nb = w->nb;
-	dim3 block(kTile, w->kc);
+	dim3 block(kTile, kMaxChunk);  // 16 warps whatever Kc is: the box staging is written for exactly this many threads
 	int per_sm = 0;
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true> : (const void*)sor_gs_tiled_kernel<true, false>)
 	                          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true> : (const void*)sor_gs_tiled_kernel<false, false>);
-	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * w->kc, 0));
+	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * kMaxChunk, 0));
 	if (const char* e = getenv("FLIPGPU_TILE_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
 	int blocks = std::min(w->n_tiles, std::max(1, per_sm) * w->sms);
 	void* args[] = {&A};
