@@ -381,13 +381,18 @@ def product_arm(args, rank, world, local_rank):
             dist.barrier()
 
     # ---- device-resident throughput ("value"): K x flip_step, state resident in HBM
+    clocks = ClockSampler(local_rank)
+    clocks.start()                       # nvidia-smi needs ~0.3 s to deliver its first sample: start it before the warm-up
     sim.simulate(**kw, n_steps=args.warmup, update_colors=False)
+    barrier()
+    time.sleep(0.4)
+    sim.simulate(**kw, n_steps=min(args.warmup, 3), update_colors=False)   # second warm-up burst: the clocks are ramped when timing starts
+    barrier()
+    reseed()
     barrier()
     sim.enable_timings(True)
     sim.reset_timings()
     launches0 = sim.launch_count
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     ms, done, launches = 0.0, 0, 0
     while done < args.steps:
         n = min(SEG, args.steps - done)

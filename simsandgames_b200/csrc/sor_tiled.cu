@@ -28,7 +28,8 @@ namespace fg {
 
 constexpr int kTile = 32;        // T: one warp spans a tile row of the skewed square
 constexpr int kMaxChunk = 16;    // Kc <= kMaxChunk <= T
-constexpr int kBoxW = kTile + kMaxChunk;  // even: lane stride kBoxW-1 is odd -> conflict-free diagonals
+constexpr int kBoxW = kTile + kMaxChunk + 2;  // 50: lanes of one iteration stride by W-1 = 49 (odd, conflict-free) and lanes of
+                                             // different iterations packed into one warp collide only for (da,dk) = (2,10), (4,-12) ...
 
 struct TiledArgs {
 	int nf, ns;
@@ -52,13 +53,16 @@ __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
 	for (long long spins = 0; *((volatile const int*)flag) != epoch && spins < (1ll << 25); spins++) __nanosleep(64);
 }
 
-template <bool XFAST, bool DRIFT>
-__global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_tiled_kernel(TiledArgs A) {
-	__shared__ float s_vf[kBoxW * kBoxW];
-	__shared__ float s_vs[kBoxW * kBoxW];
-	__shared__ float s_p[kBoxW * kBoxW];
-	__shared__ float s_dr[DRIFT ? kBoxW * kBoxW : 1];
-	__shared__ unsigned char s_code[kBoxW * kBoxW];
+template <bool XFAST, bool DRIFT, int KW>  // KW warps per CTA (>= iterations per chunk)
+__global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_kernel(TiledArgs A) {
+	// dynamic shared memory (> 48 KB with the drift term): four float planes and the cell code as a 32-bit word per cell
+	// (a byte plane would put several lanes of a diagonal into one bank)
+	extern __shared__ float smem_tile[];
+	float* s_vf = smem_tile;
+	float* s_vs = s_vf + kBoxW * kBoxW;
+	float* s_p = s_vs + kBoxW * kBoxW;
+	unsigned* s_code = reinterpret_cast<unsigned*>(s_p + kBoxW * kBoxW);
+	float* s_dr = reinterpret_cast<float*>(s_code + kBoxW * kBoxW);  // only touched when DRIFT
 	__shared__ int s_tile;
 	const int tid = threadIdx.y * kTile + threadIdx.x;
 	const int nthreads = kTile * blockDim.y;
@@ -96,9 +100,9 @@ __global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_tiled_kernel(Tile
 		// issued before any is consumed, so the box costs one L2 round trip instead of one per element: the tile sits on
 		// the critical path of the wavefront and its fixed costs are paid once per wave.
 		{
-			constexpr int kRounds = (kBoxW * kBoxW + kTile * kMaxChunk - 1) / (kTile * kMaxChunk);
+			constexpr int kRounds = (kBoxW * kBoxW + kTile * KW - 1) / (kTile * KW);
 			float r_vf[kRounds], r_vs[kRounds], r_p[kRounds], r_dr[kRounds];
-			unsigned char r_cd[kRounds];
+			unsigned r_cd[kRounds];
 #pragma unroll
 			for (int r = 0; r < kRounds; r++) {
 				int e = tid + r * nthreads;
@@ -127,32 +131,38 @@ __global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_tiled_kernel(Tile
 		// Lane a owns local column a: it is busy on steps t in [a, a+T-1] and walks down its box column by one
 		// row per step.  Cells outside the grid interior carry code 0 (sor_prep_kernel / the box fill), so no
 		// bounds tests are needed here.
-		const int a = threadIdx.x;
+		// Work items of step t are the cells (a, t-a) of every iteration k < kq with a in [alo, ahi].  They are dealt out
+		// densely over the CTA (item = thread id), so on the ramps of the skewed square -- where a diagonal holds only a few
+		// cells -- whole warps have nothing to issue instead of every warp issuing for a few lanes.
 		for (int t = 0; t < 2 * kTile - 1; t++) {
-			if (t >= a && t < a + kTile) {
-				for (int k = threadIdx.y; k < kq; k += blockDim.y) {
+			const int alo = max(0, t - (kTile - 1)), cnt = min(kTile - 1, t) - alo + 1;
+			if (tid < cnt * kq) {
+				const int k = (int)(((float)tid + 0.5f) * (1.f / (float)cnt));  // tid / cnt: the quotient is >= 1/64 away from an integer
+				const int a = alo + (tid - k * cnt);
+				{
 					// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
 					int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
 					// every operand is fetched before the activity test: one shared-memory round trip per step instead of two
 					unsigned cd = s_code[e];
 					float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[e + kBoxW], pp = s_p[e];
 					float dr = DRIFT ? s_dr[e] : 0.f;
-					if (!(cd & 1u)) continue;
-					float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
-					if (DRIFT) div -= dr;        // the stored term is max(0, density-rest): subtracting 0 is exact
-					if (cd == 31u) {             // all four neighbours open: s_sum = 4 and x/4 == x*0.25 exactly
-						float pv = (-div * 0.25f) * A.omega;
-						s_p[e] = pp + A.cp * pv;
-						s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[e + kBoxW] = vsp + pv;
-					} else {
-						float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
-						float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
-						float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
-						float pv = -div / ssum;
-						pv *= A.omega;
-						s_p[e] = pp + A.cp * pv;
-						s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
-						s_vs[e] = vsc - ssm * pv; s_vs[e + kBoxW] = vsp + ssp * pv;
+					if (cd & 1u) {
+						float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
+						if (DRIFT) div -= dr;        // the stored term is max(0, density-rest): subtracting 0 is exact
+						if (cd == 31u) {             // all four neighbours open: s_sum = 4 and x/4 == x*0.25 exactly
+							float pv = (-div * 0.25f) * A.omega;
+							s_p[e] = pp + A.cp * pv;
+							s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[e + kBoxW] = vsp + pv;
+						} else {
+							float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
+							float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
+							float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+							float pv = -div / ssum;
+							pv *= A.omega;
+							s_p[e] = pp + A.cp * pv;
+							s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
+							s_vs[e] = vsc - ssm * pv; s_vs[e + kBoxW] = vsp + ssp * pv;
+						}
 					}
 				}
 			}
@@ -328,15 +338,23 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
 	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega; A.prof = w->prof;
 	A.act = w->act; A.na = w->na; A.nb = w->nb;
-	dim3 block(kTile, kMaxChunk);  // 16 warps whatever Kc is: the box staging is written for exactly this many threads
+	const int kw = w->kc <= 8 ? 8 : 16;  // warps per CTA: the box staging is unrolled for exactly this many threads
+	dim3 block(kTile, kw);
 	int per_sm = 0;
-	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true> : (const void*)sor_gs_tiled_kernel<true, false>)
-	                          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true> : (const void*)sor_gs_tiled_kernel<false, false>);
-	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * kMaxChunk, 0));
+	const void* fn;
+	if (kw == 8)
+		fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, 8> : (const void*)sor_gs_tiled_kernel<true, false, 8>)
+		              : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, 8> : (const void*)sor_gs_tiled_kernel<false, false, 8>);
+	else
+		fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, 16> : (const void*)sor_gs_tiled_kernel<true, false, 16>)
+		              : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, 16> : (const void*)sor_gs_tiled_kernel<false, false, 16>);
+	const size_t tile_smem = (size_t)kBoxW * kBoxW * 4 * (use_drift ? 5 : 4);
+	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * kw, tile_smem));
 	if (const char* e = getenv("FLIPGPU_TILE_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
 	int blocks = std::min(w->n_tiles, std::max(1, per_sm) * w->sms);
 	void* args[] = {&A};
-	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, 0, st));
+	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, tile_smem, st));
 	if (lc) lc->n += 2;
 	return FLIPGPU_OK;
 }
