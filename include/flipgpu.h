@@ -127,6 +127,14 @@ int flip_phase_p2g(FlipSim* sim);                                               
 int flip_phase_solve(FlipSim* sim, int iters, float dt, float omega, int drift, int order); /* :451-495 */
 int flip_phase_g2p(FlipSim* sim, float flip_ratio);                                  /* :404-429 */
 int flip_phase_colors(FlipSim* sim);                                                 /* :498-557 */
+/* Reference-order ("exact") mode for parity runs on small scenes: the separation sweeps run in the reference's serial
+ * particle order (level-scheduled, flip_fluid.h:203-250 incl. Q1), the P2G adds of every node run in caller order
+ * (:398-403, :315-318) and the rest density is the serial running sum of :321-332.  Together with
+ * FLIP_SOLVER_LEX_WAVEFRONT a whole flip_step is then bit-identical to FlipFluid::simulate.  Much slower. */
+int flip_set_exact_order(FlipSim* sim, int on);
+/* levels of the last serial-order separation schedule; drifted != 0 if a particle left the 1-cell neighbourhood of its
+ * bin during the sweeps (the schedule's validity assumption; never seen on the reference scenes) */
+int flip_get_exact_order_info(FlipSim* sim, int* levels, int* drifted);
 int flip_get_scalar(FlipSim* sim, int which, float* out);
 int flip_set_rest_density(FlipSim* sim, float rest);
 int flip_synchronize(FlipSim* sim);

@@ -221,6 +221,15 @@ class FlipFluidGPU:
     def updateColors(self):
         _check(self._lib.flip_phase_colors(self._h), "flip_phase_colors")
 
+    def set_exact_order(self, on=True):
+        """reference order of every float reduction (serial-order separation, caller-order P2G, serial latch): parity mode"""
+        _check(self._lib.flip_set_exact_order(self._h, int(on)), "flip_set_exact_order")
+
+    def exact_order_info(self):
+        a, b = C.c_int(), C.c_int()
+        _check(self._lib.flip_get_exact_order_info(self._h, C.byref(a), C.byref(b)), "flip_get_exact_order_info")
+        return a.value, b.value
+
     # ---- diagnostics
     def residual(self):
         mx, rms = C.c_float(), C.c_float()

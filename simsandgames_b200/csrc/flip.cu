@@ -703,6 +703,151 @@ __global__ void k_rest_from_pair(const float* __restrict__ pair, float* __restri
 	if (threadIdx.x == 0 && *rest == 0.f && pair[1] > 0.f) *rest = pair[0] / pair[1];
 }
 
+
+// =================================================================== reference-order ("exact") mode
+// flip_set_exact_order(sim, 1): every place where the production path only changes the ORDER of floating-point
+// operations is switched to the reference's own order, so that whole steps are bit-identical to the serial CPU code
+// (with the lexicographic solver).  Meant for parity runs on small scenes; it is much slower.
+
+// ---- F3 in the reference's serial order (flip_fluid.h:203-250), made parallel by level scheduling.
+// Processing particle i reads/writes only particles of the 3x3 hash cells around its current cell, so two particles
+// whose bins are more than kDepR cells apart (Chebyshev) commute; level[i] = 1 + max level of the lower-indexed particles
+// within kDepR cells.  Running the levels in order, and the particles of one level concurrently, performs exactly the
+// serial sweep.  (kDepR = 4 assumes no particle has drifted more than one cell from its bin, which k_sep_exact checks.)
+constexpr int kDepR = 4;
+__global__ void __launch_bounds__(kThreads) k_sep_levels(Geo g, const int* __restrict__ first, const int* __restrict__ orig,
+                                                         const float2* __restrict__ binpos, const int* __restrict__ lvl_in,
+                                                         int* __restrict__ lvl_out, int* __restrict__ changed) {
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		int cx, cy;
+		hash_cell(g, binpos[t].x, binpos[t].y, &cx, &cy);
+		const int me = orig[t];
+		int lv = 0;
+		for (int yi = max(cy - kDepR, g.hy0); yi <= min(cy + kDepR, g.hy1 - 1); yi++) {
+			int a = first[max(cx - kDepR, 0) + g.pnx * yi], b = first[min(cx + kDepR, g.pnx - 1) + g.pnx * yi + 1];
+			for (int j = a; j < b; j++)
+				if (orig[j] < me) lv = max(lv, lvl_in[j]);
+		}
+		lv += 1;
+		lvl_out[t] = lv;
+		if (lv != lvl_in[t]) *changed = 1;
+	}
+}
+template <bool COLORS>
+__global__ void __launch_bounds__(kThreads) k_sep_exact(Geo g, const int* __restrict__ first, const int* __restrict__ level, int cur_level,
+                                                        float2* __restrict__ pos, float* __restrict__ col, const float2* __restrict__ binpos,
+                                                        int* __restrict__ drift_flag) {
+	const float min_dist = 2.f * g.r;
+	const float min_dist_sq = min_dist * min_dist;
+	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
+		if (level[t] != cur_level) continue;
+		float px = pos[t].x, py = pos[t].y;
+		int pxi = (int)(px * g.p_inv), pyi = (int)(py * g.p_inv);
+		{	// the level schedule is only valid while particles stay within one cell of their bin
+			int bx, by;
+			hash_cell(g, binpos[t].x, binpos[t].y, &bx, &by);
+			if (abs(clampi(pxi, 0, g.pnx - 1) - bx) > 1 || abs(clampi(pyi, g.hy0, g.hy1 - 1) - by) > 1) *drift_flag = 1;
+		}
+		int x0 = max(pxi - 1, 0), y0 = max(pyi - 1, g.hy0);
+		int x1 = min(pxi + 1, g.pnx - 1), y1 = min(pyi + 1, g.hy1 - 1);
+		for (int xi = x0; xi <= x1; xi++)
+			for (int yi = y0; yi <= y1; yi++) {
+				int c = xi + g.pnx * yi;
+				for (int j = first[c]; j < first[c + 1]; j++) {
+					if (j == t) continue;
+					float dx = pos[j].x - px, dy = pos[j].y - py;
+					float d2 = dx * dx + dy * dy;
+					if (d2 > min_dist_sq || d2 == 0.f) continue;
+					float d = sqrtf(d2);
+					float sc = .5f * (min_dist - d) / d;
+					dx *= sc; dy *= sc;
+					pos[t].x -= dx;       // :234-235: i moves in memory ...
+					pos[t].y -= dy;
+					pos[j].x += dx;       // :236 (Q1): the partner only in x,
+					py += dy;             //            the local py drifts instead
+					if (COLORS)
+						for (int ch = 0; ch < 3; ch++) {  // :239-245
+							float c0 = col[ch + 3 * (size_t)t], c1 = col[ch + 3 * (size_t)j];
+							float mean = (c0 + c1) / 2.f;
+							col[ch + 3 * (size_t)t] = c0 + .001f * (mean - c0);
+							col[ch + 3 * (size_t)j] = c1 + .001f * (mean - c1);
+						}
+				}
+			}
+	}
+}
+
+// ---- F6/F7 with the adds of every node in CALLER order: the lists of the four base cells are merged by caller index
+__global__ void __launch_bounds__(kThreads) k_fixup_grid_by_id(int n_cells, const int* __restrict__ gcount, const int* __restrict__ gfirst,
+                                                               int* __restrict__ gidx, const int* __restrict__ orig) {
+	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+		int n = gcount[c];
+		if (n < 2) continue;
+		int b = gfirst[c];
+		for (int i = 1; i < n; i++) {
+			int v = gidx[b + i], key = orig[v], j = i - 1;
+			while (j >= 0 && orig[gidx[b + j]] > key) { gidx[b + j + 1] = gidx[b + j]; j--; }
+			gidx[b + j + 1] = v;
+		}
+	}
+}
+__global__ void __launch_bounds__(256) k_p2g_gather_exact(Geo g, const int* __restrict__ gfirst, const int* __restrict__ gidx,
+                                                          const int* __restrict__ orig, const float2* __restrict__ pos,
+                                                          const float2* __restrict__ vel, const int* __restrict__ cell_type,
+                                                          float* __restrict__ u, float* __restrict__ v, float* __restrict__ prev_u,
+                                                          float* __restrict__ prev_v, float* __restrict__ dens, float* __restrict__ p) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int j = g.ny0 + blockIdx.y * blockDim.y + threadIdx.y;
+	if (i >= g.nx || j >= g.ny1) return;
+	// heads of the (up to) four base-cell lists that can reach this node
+	int head[4], end[4];
+	int nl = 0;
+	for (int cy = max(j - 1, g.gy0); cy <= j; cy++)
+		for (int cx = max(i - 1, 0); cx <= i; cx++) { head[nl] = gfirst[cx + g.nx * cy]; end[nl] = gfirst[cx + g.nx * cy + 1]; nl++; }
+	float su = 0.f, sv = 0.f, swu = 0.f, swd = 0.f;
+	for (;;) {
+		int best = -1, best_id = 0x7fffffff;
+		for (int l = 0; l < nl; l++)
+			if (head[l] < end[l]) { int id = orig[gidx[head[l]]]; if (id < best_id) { best_id = id; best = l; } }
+		if (best < 0) break;
+		int t = gidx[head[best]++];
+		float2 pp = pos[t];
+		Stencil st = make_stencil(g, pp.x, pp.y);
+		bool mx0 = st.x0 == i, mx1 = st.x1 == i, my0 = st.y0 == j, my1 = st.y1 == j;
+		if (!((mx0 | mx1) & (my0 | my1))) continue;
+		float2 pv = vel[t];
+		// velocity splat order of :400-403 (nr0, nr1, nr2, nr3) ...
+		if (mx0 & my0) { su += pv.x * st.w0; sv += pv.y * st.w0; swu += st.w0; }
+		if (mx1 & my0) { su += pv.x * st.w1; sv += pv.y * st.w1; swu += st.w1; }
+		if (mx1 & my1) { su += pv.x * st.w2; sv += pv.y * st.w2; swu += st.w2; }
+		if (mx0 & my1) { su += pv.x * st.w3; sv += pv.y * st.w3; swu += st.w3; }
+		// ... and the density order of :315-318 (x0y0, x1y0, x0y1, x1y1), which differs on aliased border cells
+		if (mx0 & my0) swd += st.w0;
+		if (mx1 & my0) swd += st.w1;
+		if (mx0 & my1) swd += st.w3;
+		if (mx1 & my1) swd += st.w2;
+	}
+	int c = i + g.nx * j;
+	if (swu > 0.f) { su /= swu; sv /= swu; }
+	int ct = cell_type[c];
+	bool solid = ct == SOLID_CELL;
+	if (solid || (i > 0 && cell_type[c - 1] == SOLID_CELL)) su = u[c];
+	if (solid || (j > 0 && cell_type[c - g.nx] == SOLID_CELL)) sv = v[c];
+	u[c] = su; v[c] = sv;
+	prev_u[c] = su; prev_v[c] = sv;
+	dens[c] = swd;
+	p[c] = 0.f;
+}
+// the latch as the serial running sum of :321-332
+__global__ void k_rest_latch_serial(int n, const int* __restrict__ cell_type, const float* __restrict__ dens, float* __restrict__ rest) {
+	if (threadIdx.x != 0 || blockIdx.x != 0 || *rest != 0.f) return;
+	float sum = 0.f;
+	int cnt = 0;
+	for (int c = 0; c < n; c++)
+		if (cell_type[c] == FLUID_CELL) { sum += dens[c]; cnt++; }
+	if (cnt > 0) *rest = sum / cnt;
+}
+
 }  // namespace fg
 
 // =================================================================== host side
@@ -745,6 +890,9 @@ struct FlipSim {
 	int n_owned = 0;
 	long long exchanges = 0;
 	bool s_binary = true;       // every s[] is 0 or 1 (tracked on upload)
+	bool exact_order = false;   // flip_set_exact_order: reference order of every float reduction (parity runs)
+	int *lvl[2] = {nullptr, nullptr}, *d_flags = nullptr;  // level schedule of the serial-order separation
+	int sep_levels = 0;
 	bool identity = true;       // slot order == caller order
 	bool bins_valid = false;
 	bool rest_seen = false;
@@ -876,9 +1024,61 @@ int integrate_and_bin(FlipSim* f, bool integrate, bool bin, float dt, float grav
 	return FLIPGPU_OK;
 }
 
+
+// serial-order separation (exact mode): level schedule from the bins, then the levels one after the other
+int separate_exact(FlipSim* f, int iters, bool colors) {
+	Geo g = geo(f);
+	if (g.np == 0 || iters <= 0) return FLIPGPU_OK;
+	if (colors) FG_TRY(ensure_colors(f));
+	const int c = f->cur;
+	const size_t M = (size_t)std::max(f->d.max_particles, 1);
+	if (!f->lvl[0]) {
+		FG_CUDA(cudaMalloc(&f->lvl[0], M * 4));
+		FG_CUDA(cudaMalloc(&f->lvl[1], M * 4));
+		FG_CUDA(cudaMalloc(&f->d_flags, 4 * sizeof(int)));
+	}
+	// positions at binning time = the current ones (separation follows the binning directly); keep a copy for the schedule
+	float2* binpos = f->pos[1 - c];
+	FG_CUDA(cudaMemcpyAsync(binpos, f->pos[c], (size_t)g.np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st));
+	FG_CUDA(cudaMemsetAsync(f->lvl[0], 0, (size_t)g.np * 4, f->st));
+	int a = 0, levels = 0;
+	for (int round = 0; round < g.np + 2; round++) {  // Jacobi relaxation of the longest-path problem: converges in (depth) rounds
+		FG_CUDA(cudaMemsetAsync(f->d_flags, 0, sizeof(int), f->st));
+		k_sep_levels<<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, f->orig[c], binpos, f->lvl[a], f->lvl[1 - a], f->d_flags);
+		f->lc.n++;
+		a = 1 - a;
+		int changed = 0;
+		if ((round & 7) == 7 || round < 2) {  // poll the flag every few rounds
+			FG_CUDA(cudaMemcpyAsync(&changed, f->d_flags, sizeof(int), cudaMemcpyDeviceToHost, f->st));
+			FG_CUDA(cudaStreamSynchronize(f->st));
+			if (!changed && round >= 1) {
+				// one more quiet round proves the fixed point (the flag only covers the last round)
+				break;
+			}
+		}
+	}
+	{	// number of levels = max level
+		std::vector<int> h(g.np);
+		FG_CUDA(cudaMemcpyAsync(h.data(), f->lvl[a], (size_t)g.np * 4, cudaMemcpyDeviceToHost, f->st));
+		FG_CUDA(cudaStreamSynchronize(f->st));
+		for (int v : h) levels = std::max(levels, v);
+	}
+	f->sep_levels = levels;
+	FG_CUDA(cudaMemsetAsync(f->d_flags + 1, 0, sizeof(int), f->st));
+	for (int it = 0; it < iters; it++)
+		for (int L = 1; L <= levels; L++) {
+			if (colors) k_sep_exact<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, f->lvl[a], L, f->pos[c], f->col[c], binpos, f->d_flags + 1);
+			else k_sep_exact<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, f->lvl[a], L, f->pos[c], nullptr, binpos, f->d_flags + 1);
+			f->lc.n++;
+		}
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
 int separate(FlipSim* f, int iters, bool colors) {
 	Geo g = geo(f);
 	if (g.np == 0) return FLIPGPU_OK;
+	if (f->exact_order) return separate_exact(f, iters, colors);
 	if (colors) FG_TRY(ensure_colors(f));
 	// Sweeps ping-pong between the two position buffers; velocities (and ids) stay in buffer `cur`,
 	// so after an odd number of sweeps the result is copied back rather than swapping every array.
@@ -921,7 +1121,8 @@ int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float 
 		running_sum(f, f->gcount + goff, C, f->gfirst + goff);
 		if (g.np > 0) {
 			k_fill_grid<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->keys, f->gfirst, f->src);
-			k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src);
+			if (f->exact_order) k_fixup_grid_by_id<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src, f->orig[c]);
+			else k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src);
 			f->lc.n += 2;
 		}
 	}
@@ -936,11 +1137,19 @@ int p2g(FlipSim* f) {
 	int c = f->cur;
 	dim3 block(32, 8);
 	dim3 grid(cdiv(g.nx, block.x), cdiv(g.ny1 - g.ny0, block.y));
-	k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
-	                                        f->prev_u, f->prev_v, f->dens, f->p);
+	if (f->exact_order)
+		k_p2g_gather_exact<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->orig[c], f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
+		                                              f->prev_u, f->prev_v, f->dens, f->p);
+	else
+		k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
+		                                        f->prev_u, f->prev_v, f->dens, f->p);
 	f->lc.n++;
 	if (!f->rest_seen && f->sharded) {
 		FG_TRY(shard_rest_latch(f));
+	} else if (!f->rest_seen && f->exact_order) {
+		k_rest_latch_serial<<<1, 32, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest);
+		f->lc.n++;
+		FG_CUDA(cudaMemcpyAsync(f->h_pinned, f->d_rest, sizeof(float), cudaMemcpyDeviceToHost, f->st));
 	} else if (!f->rest_seen) {
 		k_rest_partials<<<kPartials, 256, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest, f->d_partials);
 		k_rest_latch<<<1, 32, 0, f->st>>>(kPartials, f->d_partials, f->d_rest);
@@ -1266,6 +1475,7 @@ int flip_destroy(FlipSim* f) {
 	if (f->comm) g_nccl.CommDestroy(f->comm);
 	for (int k = 0; k < 2; k++) { cudaFree(f->send_pos[k]); cudaFree(f->send_vel[k]); cudaFree(f->send_id[k]); }
 	cudaFree(f->d_counters);
+	cudaFree(f->lvl[0]); cudaFree(f->lvl[1]); cudaFree(f->d_flags);
 	if (f->h_counters) cudaFreeHost(f->h_counters);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
 	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
@@ -1638,6 +1848,22 @@ int flip_set_rest_density(FlipSim* f, float rest) {
 	return FLIPGPU_OK;
 }
 
+int flip_set_exact_order(FlipSim* f, int on) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded || !on, FLIPGPU_ESTATE, "the reference-order mode is a single-GPU parity mode");
+	f->exact_order = on != 0;
+	return FLIPGPU_OK;
+}
+int flip_get_exact_order_info(FlipSim* f, int* levels, int* drifted) {
+	FG_CHECK(f && levels && drifted, FLIPGPU_EINVAL, "null argument");
+	DeviceGuard guard(f->device);
+	*levels = f->sep_levels; *drifted = 0;
+	if (f->d_flags) {
+		FG_CUDA(cudaMemcpyAsync(drifted, f->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, f->st));
+		FG_CUDA(cudaStreamSynchronize(f->st));
+	}
+	return FLIPGPU_OK;
+}
 int flip_synchronize(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	DeviceGuard guard(f->device);

@@ -492,3 +492,57 @@ def test_async_readback_matches_blocking_readback():
     sim.readback_wait()
     assert_bit_equal(frames[1].numpy(), want[3], "last frame")
     assert_bit_equal(frames[0].numpy(), want[2], "previous frame")
+
+
+# ------------------------------------------------------------------ reference-order mode: whole steps bit-identical
+def test_exact_order_separation_phase_bit_identical(tank_states):
+    """The level-scheduled serial-order sweep reproduces pushParticlesApart (flip_fluid.h:165-251, Q1 and Q6 included)."""
+    states, p, g = tank_states
+    for step in (9, 29, 60):
+        o = clone_oracle(states[step], g)
+        sim = gpu_like(o, g)
+        sim.set_exact_order(True)
+        o.integrate(p["dt"], p["gravity"]); sim.integrateParticles(p["dt"], p["gravity"])
+        o.push_apart(2)
+        sim.pushParticlesApart(2, update_colors=True)
+        P = o.num_particles
+        assert_bit_equal(sim.readback("particle_pos"), o.particle_pos[:2 * P], f"serial-order separation, step {step}")
+        assert_bit_equal(sim.readback("particle_color"), o.particle_color[:3 * P], f"colour diffusion, step {step}")
+        levels, drifted = sim.exact_order_info()
+        assert levels > 1 and drifted == 0
+
+
+def test_exact_order_p2g_bit_identical(tank_states):
+    states, p, g = tank_states
+    for step in (0, 29, 60):
+        o = clone_oracle(states[step], g)
+        o.integrate(p["dt"], p["gravity"]); o.push_apart(2); o.collide(p["ox"], p["oy"], 0, 0, p["orad"])
+        sim = gpu_like(o, g)
+        sim.set_exact_order(True)
+        if step == 0:
+            sim.particle_rest_density = 0.0; o.set_rest_density(0.0)
+        o.transfer(True); o.update_density()
+        sim.transferVelocitiesToGrid()
+        for name in ("u", "v", "particle_density", "cell_type"):
+            assert_bit_equal(sim.readback(name), getattr(o, name), f"caller-order P2G {name}, step {step}")
+        assert float(sim.particle_rest_density) == float(o.particle_rest_density)   # serial running sum
+
+
+@pytest.mark.parametrize("steps", [1, 10, 120, 1000])   # 1000 = BASELINE configs[0]
+def test_exact_order_whole_steps_bit_identical_to_reference(steps):
+    """FlipFluid::simulate (flip_fluid.h:560-581) on the default tank, from the initial lattice: every state array the
+    reference keeps is reproduced bit for bit after `steps` whole steps (reference-order mode + lexicographic solver)."""
+    o, p, g = co.make_flip_scene("default", oracle_kind="port")
+    sim, kw, _ = sg.scenes.make_flip_tank("default")
+    sim.set_exact_order(True)
+    o.simulate(**p, n_steps=steps)
+    sim.simulate(**kw, n_steps=steps, solver_order=sg.LEX_WAVEFRONT, update_colors=True)
+    P = o.num_particles
+    for name, n in (("particle_pos", 2 * P), ("particle_vel", 2 * P), ("particle_color", 3 * P)):
+        assert_bit_equal(sim.readback(name), getattr(o, name)[:n], f"{name} after {steps} steps")
+    for name in ("u", "v", "p", "prev_u", "prev_v", "particle_density", "cell_type", "cell_color",
+                 "num_cell_particles", "first_cell_particle"):
+        assert_bit_equal(sim.readback(name), getattr(o, name), f"{name} after {steps} steps")
+    assert_bit_equal(sim.readback("cell_particle_ids"), o.cell_particle_ids[:P], "cell_particle_ids")
+    assert float(sim.particle_rest_density) == float(o.particle_rest_density)
+    assert sim.exact_order_info()[1] == 0
