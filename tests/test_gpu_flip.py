@@ -546,3 +546,25 @@ def test_exact_order_whole_steps_bit_identical_to_reference(steps):
     assert_bit_equal(sim.readback("cell_particle_ids"), o.cell_particle_ids[:P], "cell_particle_ids")
     assert float(sim.particle_rest_density) == float(o.particle_rest_density)
     assert sim.exact_order_info()[1] == 0
+
+
+@pytest.mark.parametrize("case,kind,N", [("flip_default", "default", None), ("flip_synthetic_64", "synthetic", 64)])
+def test_exact_order_matches_committed_reference_goldens(case, kind, N):
+    """The CUDA path against the golden hashes that tests/golden/make_golden.py took from the UNMODIFIED reference
+    (oracle/_ref) -- no oracle in the loop: sha256 of every state array after 1, 5 and 20 (12) whole steps."""
+    import json, os
+    from tests.golden.make_golden import sha
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))[case]
+    sim, kw, geo = sg.scenes.make_flip_tank(kind, N=N)
+    sim.set_exact_order(True)
+    P = sim.num_particles
+    assert P == gold["dims"]["num_particles"] and (sim.f_num_x, sim.f_num_y) == (gold["dims"]["f_num_x"], gold["dims"]["f_num_y"])
+    assert sha(sim.readback("particle_pos")) == gold["scene"]["particle_pos"] and sha(sim.readback("s")) == gold["scene"]["s"]
+    done = 0
+    for c in sorted(int(k) for k in gold["steps"]):
+        sim.simulate(**kw, n_steps=c - done, solver_order=sg.LEX_WAVEFRONT, update_colors=True); done = c
+        rec = gold["steps"][str(c)]
+        for name in ("particle_pos", "particle_vel", "particle_color", "u", "v", "p", "prev_u", "particle_density", "cell_type",
+                     "cell_color", "num_cell_particles", "first_cell_particle", "cell_particle_ids"):
+            assert sha(sim.readback(name)) == rec[name], (case, c, name)
+        assert int(np.float32(sim.particle_rest_density).view(np.int32)) == rec["rest_density_bits"]
