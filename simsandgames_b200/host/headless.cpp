@@ -7,6 +7,8 @@
 //   headless flip  default      <steps>
 //   headless flip  synthetic N  <steps> [obstacle]
 //   headless euler X Y ITERS    <steps>
+// Optional trailing  --ppm FILE  writes the frame the UI would draw after the last step (main.cpp:171-196 /
+// fluid_ui.h:126-151) as a binary PPM: the reference's only "test" is looking at that frame.
 // Prints one JSON line: sizes, wall time, and checksums of the state the UI would draw.
 #include <chrono>
 #include <cmath>
@@ -16,6 +18,7 @@
 #include <string>
 #include <type_traits>
 #include <utility>
+#include <vector>
 
 #ifdef WITH_REFERENCE
 #include "flip_fluid.h"  // -I/root/reference/flip_fluid/src (unmodified)
@@ -29,6 +32,42 @@ template <class T, class = void> struct has_mark_dirty : std::false_type {};
 template <class T> struct has_mark_dirty<T, std::void_t<decltype(std::declval<T&>().mark_dirty())>> : std::true_type {};
 template <class Sim> void host_wrote(Sim& s) { if constexpr (has_mark_dirty<Sim>::value) s.mark_dirty(); }
 template <class Sim> void host_reads(Sim& s) { if constexpr (has_mark_dirty<Sim>::value) s.pull_render_state(); }
+
+
+static const char* g_ppm_path = nullptr;
+
+static void write_ppm(const char* path, int w, int h, const std::vector<unsigned char>& rgb) {
+	FILE* fp = std::fopen(path, "wb");
+	if (!fp) { std::perror(path); return; }
+	std::fprintf(fp, "P6\n%d %d\n255\n", w, h);
+	std::fwrite(rgb.data(), 1, rgb.size(), fp);
+	std::fclose(fp);
+}
+static unsigned char to_byte(float c) { c = c < 0 ? 0 : (c > 1 ? 1 : c); return (unsigned char)(c * 255.f + .5f); }
+
+// the frame of flip_fluid/src/main.cpp:171-196 at one pixel per 1/px_per_cell of a cell: density cells (cell_color) as the
+// background, then every particle as a dot in its particle_color, then the obstacle outline in red
+template <class Sim> void dump_flip_frame(Sim& f, const char* path, float ox, float oy, float orad) {
+	const int px = 4, w = f.f_num_x * px, h = f.f_num_y * px;
+	std::vector<unsigned char> img((size_t)w * h * 3);
+	for (int y = 0; y < h; y++)
+		for (int x = 0; x < w; x++) {
+			int c = f.fIX(x / px, y / px);
+			for (int k = 0; k < 3; k++) img[3 * ((size_t)y * w + x) + k] = to_byte(f.cell_color[3 * c + k] * .35f);
+		}
+	const float scale = px / f.h;
+	for (int i = 0; i < f.num_particles; i++) {
+		int x = (int)(f.particle_pos[2 * i] * scale), y = (int)(f.particle_pos[2 * i + 1] * scale);
+		if (x < 0 || x >= w || y < 0 || y >= h) continue;
+		for (int k = 0; k < 3; k++) img[3 * ((size_t)y * w + x) + k] = to_byte(f.particle_color[3 * i + k]);
+	}
+	if (orad > 0)
+		for (int a = 0; a < 720; a++) {
+			int x = (int)((ox + orad * std::cos(a * 3.14159265f / 360)) * scale), y = (int)((oy + orad * std::sin(a * 3.14159265f / 360)) * scale);
+			if (x >= 0 && x < w && y >= 0 && y < h) { img[3 * ((size_t)y * w + x)] = 255; img[3 * ((size_t)y * w + x) + 1] = 0; img[3 * ((size_t)y * w + x) + 2] = 0; }
+		}
+	write_ppm(path, w, h, img);
+}
 
 struct FlipScene {
 	float width, height, spacing, radius, dt;
@@ -72,6 +111,9 @@ template <class Sim> int run_flip(const FlipScene& sc, int steps) {
 		for (int i = 0; i < max_particles; i++) fluid->particle_color[3 * i] = fluid->particle_color[3 * i + 1] = 0;
 	}
 #endif
+#ifndef WITH_REFERENCE
+	if (std::getenv("FLIPGPU_EXACT")) flipgpu::check(flip_set_exact_order(fluid->handle(), 1), "flip_set_exact_order");  // parity runs
+#endif
 	fluid->num_particles = num_x * num_y;
 	int p = 0;
 	for (int i = 0; i < num_x; i++)
@@ -93,6 +135,7 @@ template <class Sim> int run_flip(const FlipScene& sc, int steps) {
 		fluid->simulate(sc.dt, 9.81f, .9f, sc.iters, 2, 1.9f, true, true, sc.obstacle_x, sc.obstacle_y, 0.f, 0.f, sc.obstacle_radius);
 	host_reads(*fluid);  // what the renderer draws: particle_pos, particle_color, cell_color (main.cpp:173-194)
 	double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (g_ppm_path) dump_flip_frame(*fluid, g_ppm_path, sc.obstacle_x, sc.obstacle_y, sc.obstacle ? sc.obstacle_radius : 0.f);
 	double sx = 0, sy = 0, sc_b = 0, cell = 0;
 	for (int i = 0; i < fluid->num_particles; i++) {
 		sx += fluid->particle_pos[2 * i]; sy += fluid->particle_pos[2 * i + 1]; sc_b += fluid->particle_color[3 * i + 2];
@@ -147,6 +190,17 @@ template <class Sim> int run_euler(int x, int y, int iters, int steps) {
 	}
 	host_reads(*fluid);
 	double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (g_ppm_path) {  // grayscale smoke, solid cells left black (fluid_ui.h:129-150), image x = i, y = j
+		int w = fluid->getNumX(), h = fluid->getNumY();
+		std::vector<unsigned char> img((size_t)w * h * 3, 0);
+		for (int i = 0; i < w; i++)
+			for (int j = 0; j < h; j++) {
+				if (fluid->solid[fluid->ix(i, j)]) continue;
+				unsigned char v = to_byte(fluid->m[fluid->ix(i, j)]);
+				for (int k = 0; k < 3; k++) img[3 * ((size_t)j * w + i) + k] = v;
+			}
+		write_ppm(g_ppm_path, w, h, img);
+	}
 	double sm = 0, sp = 0;
 	for (int c = 0; c < fluid->getNumCells(); c++) { sm += fluid->m[c]; sp += std::fabs(fluid->pressure[c]); }
 	double updates = (double)(fluid->getNumX() - 2) * (fluid->getNumY() - 2) * iters * steps;
@@ -159,6 +213,8 @@ template <class Sim> int run_euler(int x, int y, int iters, int steps) {
 #endif
 
 int main(int argc, char** argv) {
+	for (int i = 1; i + 1 < argc; i++)
+		if (std::string(argv[i]) == "--ppm") { g_ppm_path = argv[i + 1]; argc = i; break; }
 	if (argc < 4) {
 		std::fprintf(stderr, "usage: %s flip default <steps> | flip synthetic N <steps> [obstacle] | euler X Y ITERS <steps>\n", argv[0]);
 		return 2;

@@ -57,3 +57,31 @@ def test_euler_wind_tunnel_through_cpp_facade():
     # default order = lexicographic wavefront: bit-identical fields, so the means agree to summation noise
     assert abs(g["smoke_mean"] - float(e.m.astype(np.float64).mean())) < 1e-9
     assert abs(g["abs_pressure_mean"] - float(np.abs(e.pressure).astype(np.float64).mean())) < 1e-6 * float(np.abs(e.pressure).mean()) + 1e-9
+
+
+def test_frame_dump_identical_to_reference_frame(tmp_path):
+    """the frame the UI would draw (cell colours + particles), written by the same driver source built against
+    the CUDA facade (reference-order mode) and against the unmodified reference header: the two PPM files are identical."""
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/headless_ref not built here")
+    a, b = str(tmp_path / "gpu.ppm"), str(tmp_path / "ref.ppm")
+    env = dict(os.environ, FLIPGPU_EXACT="1")
+    out = subprocess.run([GPU_BIN, "flip", "default", "40", "--ppm", a], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr
+    out = subprocess.run([REF_BIN, "flip", "default", "40", "--ppm", b], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    ga, gb = open(a, "rb").read(), open(b, "rb").read()
+    assert len(ga) == len(gb) > 500000 and ga == gb
+
+
+def test_euler_frame_dump(tmp_path):
+    path = str(tmp_path / "smoke.ppm")
+    out = subprocess.run([GPU_BIN, "euler", "96", "72", "40", "30", "--ppm", path], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    data = open(path, "rb").read()
+    assert data.startswith(b"P6\n98 74\n255\n")
+    e = co.make_euler_scene(96, 72, oracle_kind="port")
+    e.step(40, 1 / 60.0, n_steps=30)
+    img = np.frombuffer(data[len(b"P6\n98 74\n255\n"):], np.uint8).reshape(74, 98, 3)[..., 0]
+    want = np.where(e.solid.T != 0, 0, np.clip(e.m.T, 0, 1) * 255 + .5).astype(np.uint8)
+    assert np.array_equal(img, want)
