@@ -283,6 +283,99 @@ def sharded_flip_bench(args, rank, world, local_rank):
     return info
 
 
+def synthetic_rank_lattice(N, j0, j1, build=True):
+    """The particles of the synthetic dam-break (SURVEY 8d rule; lattice of flip_fluid/src/main.cpp:47-66) whose cell row lies
+    in grid rows [j0, j1), with their global caller indices p = i*num_y + j -- without materialising the other ranks' particles.
+    Same fp32 expressions as flip_scene_tank and the device ownership test."""
+    import numpy as np
+    f32 = np.float32
+    sp = f32(3) / f32(N)
+    W = (f32(N) - f32(.5)) * sp
+    r = f32(.19) * sp
+    dt = float((f32(1) / f32(60)) * (f32(100) / f32(N)))
+    dx = f32(2) * r
+    dy = f32(np.sqrt(3.0) / 2 * float(dx))
+    num_x = int((f32(.6) * W - f32(2) * sp - f32(2) * r) / dx)
+    num_y = int((f32(.8) * W - f32(2) * sp - f32(2) * r) / dy)
+    jj = np.arange(num_y)
+    y = (sp + r) + dy * jj.astype(np.float32)
+    h_grid = max(W / f32(N), W / f32(N))                # flip_fluid.h:73 with f_num_x = f_num_y = N
+    row = np.clip(((f32(1) / h_grid) * y).astype(np.int32), 0, N - 1)
+    mine = jj[(row >= j0) & (row < j1)]
+    out = dict(sp=sp, W=W, r=r, dt=dt, num_x=num_x, num_y=num_y, P_global=num_x * num_y, n_own=int(mine.size) * num_x, h_grid=h_grid)
+    if build:
+        ii = np.arange(num_x, dtype=np.float32)[:, None]
+        pos = np.empty((num_x, mine.size, 2), np.float32)
+        pos[..., 0] = ((sp + r) + dx * ii) + np.where(mine % 2 == 0, f32(0), r).astype(np.float32)[None, :]
+        pos[..., 1] = y[mine][None, :]
+        out["pos"] = pos.reshape(-1, 2)
+        out["ids"] = (np.arange(num_x, dtype=np.int64)[:, None] * num_y + mine[None, :]).astype(np.int32).reshape(-1)
+    return out
+
+
+def s3_bench(args, rank, world, local_rank, N=16384):
+    """BASELINE configs[3]: ONE flip_fluid dam-break of N^2 = 16384^2 cells / 1 029 824 840 particles, slab-sharded over `world`
+    GPUs (a fixed global problem: ranks holding air own few particles).  Every rank builds only its own lattice rows."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import simsandgames_b200 as sg
+    from simsandgames_b200 import parallel
+    uid = parallel.broadcast_unique_id()
+    j0, j1 = parallel.slab_partition(N, world)[rank]
+    geo = synthetic_rank_lattice(N, j0, j1, build=False)
+    sp, W, r, dt, num_x, num_y, P_global, n_own, h_grid = (geo[k] for k in ("sp", "W", "r", "dt", "num_x", "num_y", "P_global", "n_own", "h_grid"))
+    cap = int(max(n_own * 1.25, 4.0e6)) + 2 * num_x * 64
+    sim = sg.FlipFluidSharded(1000.0, float(W), float(W), float(sp), float(r), cap, P_global, rank, world, unique_id=uid, device=local_rank)
+    assert (sim.f_num_x, sim.f_num_y) == (N, N) and (sim.j0, sim.j1) == (j0, j1) and np.float32(sim.h) == h_grid, (sim.f_num_x, sim.j0, sim.h, h_grid)
+    built = synthetic_rank_lattice(N, j0, j1, build=True)
+    pos, ids = built["pos"], built["ids"]
+    assert sim.owns(pos[:1000]).all()
+    sim.upload_particles(pos.reshape(-1), None, ids)
+    del pos, ids
+    w0, w1 = max(j0 - sim.halo, 0), min(j1 + sim.halo, N)
+    s = np.ones((w1 - w0, N), np.float32)
+    s[:, 0] = 0; s[:, -1] = 0
+    if w0 == 0: s[0] = 0
+    if w1 == N: s[-1] = 0
+    sim.upload_rows("s", s, w0)
+    del s
+    kw = dict(dt=dt, gravity=9.81, flip_ratio=0.9, num_pressure_iters=50, num_particle_iters=2, over_relaxation=1.9, compensate_drift=True,
+              separate_particles=True, obstacle_x=0.0, obstacle_y=0.0, obstacle_vel_x=0.0, obstacle_vel_y=0.0, obstacle_radius=0.0)
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+    sim.simulate(**kw, n_steps=args.warmup)
+    sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.simulate(**kw, n_steps=args.steps)
+    e1.record(stream)
+    sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    h_out = torch.empty(2 * cap, dtype=torch.float32).pin_memory()
+    n_now = sim.readback_owned_pos_into(h_out.data_ptr(), cap)
+    cnt = torch.tensor([n_now, n_own], dtype=torch.int64, device="cuda"); dist.all_reduce(cnt)
+    owned = [None] * world
+    dist.all_gather_object(owned, n_now)
+    assert int(cnt[0].item()) == P_global == int(cnt[1].item()), "particles lost or duplicated across ranks"
+    mem = torch.cuda.mem_get_info(local_rank)
+    if rank == 0:
+        peak, peak_src = peaks()
+        s_per_step = ms * 1e-3 / args.steps
+        step_bytes = 140.0 * P_global + (96.0 + 36.0 * 50) * float(N) * N
+        print(json.dumps({
+            "metric": METRIC, "value": P_global / s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"flip_fluid synthetic dam-break {N}^2 grid, {P_global} particles, 50 SOR iters, slab-sharded (BASELINE configs[3])",
+                       "grid": [N, N], "particles_per_gpu": owned, "solver_order": "red_black", "parallelism": f"y-slabs over {world} GPUs, NCCL halo/ghost exchange",
+                       "gpu_mem_used_GB_rank0": round((mem[1] - mem[0]) / 1e9, 1)},
+            "roofline": {"bound": "hbm", "kernel": "whole sharded step (all GPUs)", "achieved": step_bytes / s_per_step / 1e9 / world, "peak": peak,
+                         "unit": "GB/s per GPU", "frac": step_bytes / s_per_step / 1e9 / world / peak, "traffic": None, "peak_source": peak_src},
+        }), flush=True)
+    sim.close()
+    dist.destroy_process_group()
+
+
 def reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -316,6 +409,9 @@ def product_arm(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1 and args.s3:
+        s3_bench(args, rank, world, local_rank, N=16384 if args.grid == BENCH_N else args.grid)
+        return
     if world > 1:
         info = sharded_flip_bench(args, rank, world, local_rank)
         shard = sharded_solver_bench(rank, world, local_rank)
@@ -516,6 +612,7 @@ def main():
     ap.add_argument("--impl", default="flipgpu", choices=["flipgpu", "reference"])
     ap.add_argument("--grid", type=int, default=BENCH_N, help="cells per side of the synthetic dam-break (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--s3", action="store_true", help="N>1 only: BASELINE configs[3], one 16384^2 / 1.03e9-particle tank sharded over the ranks")
     ap.add_argument("--with-shard-bench", action="store_true", help="also run the sharded-solver leg at N=1 (always run for N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

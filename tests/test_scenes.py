@@ -31,3 +31,24 @@ def test_wind_tunnel_arrays_match_oracle_scene():
         o = co.make_euler_scene(x, y, oracle_kind="port")
         u, m, solid = scenes.wind_tunnel_arrays(o.num_x, o.num_y)
         assert np.array_equal(u, o.u) and np.array_equal(m, o.m) and np.array_equal(solid, o.solid)
+
+
+@pytest.mark.parametrize("N,world", [(256, 2), (256, 4), (512, 8)])
+def test_per_rank_lattice_of_the_sharded_bench_is_the_global_lattice(N, world):
+    """bench.py builds each rank's particles without materialising the others (needed at 16384^2 / 1.03e9 particles):
+    the union over ranks is exactly the global lattice of flip_scene_tank, ids included, and every particle lands on its owner."""
+    import bench
+    from simsandgames_b200 import parallel
+    g = scenes.tank_geometry("synthetic", N)
+    pos, _, P = scenes.tank_particles(g["width"], g["height"], g["spacing"], g["radius"], want_s=False)
+    pos = pos.reshape(-1, 2)
+    seen = np.zeros(P, bool)
+    for rank, (j0, j1) in enumerate(parallel.slab_partition(N, world)):
+        lat = bench.synthetic_rank_lattice(N, j0, j1)
+        assert lat["P_global"] == P and lat["dt"] == g["dt"] and lat["n_own"] == lat["ids"].size
+        assert not seen[lat["ids"]].any()
+        seen[lat["ids"]] = True
+        assert np.array_equal(lat["pos"].view(np.int32), pos[lat["ids"]].view(np.int32))
+        row = np.clip((np.float32(1) / lat["h_grid"] * lat["pos"][:, 1]).astype(np.int32), 0, N - 1)
+        assert ((row >= j0) & (row < j1)).all()
+    assert seen.all()
