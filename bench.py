@@ -248,6 +248,9 @@ def sharded_flip_bench(args, rank, world, local_rank):
     SEG = 8   # red-black at 50 sweeps leaves the regime the reference stays in a little earlier than the lexicographic order
     ms, done = 0.0, 0
     launches = 0
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks:
+        clocks.start()
     while done < args.steps:
         n = min(SEG, args.steps - done)
         reseed(); barrier()
@@ -258,6 +261,7 @@ def sharded_flip_bench(args, rank, world, local_rank):
         e1.record(stream)
         barrier()
         ms += e0.elapsed_time(e1); launches += sim.launch_count - l0; done += n
+    clk = clocks.stop() if clocks else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     # end to end with host buffers: per step the caller's grid write (s rows) goes H2D, the owned particle positions come back D2H
@@ -278,7 +282,7 @@ def sharded_flip_bench(args, rank, world, local_rank):
     j0, j1, halo, band, exchanges = sim.shard_info()
     info = dict(ms_total=ms_max, P_global=P0 * world, P_per_gpu=P0, launches=launches, e2e_ms=e2e_ms, e2e_steps=e2e_steps,
                 h2d=int(h_s.numel() * 4), d2h=int(n_own * 8), halo_rows=halo, ghost_band_rows=band, nccl_exchanges=exchanges,
-                grid=[N, N * world])
+                grid=[N, N * world], clocks=clk)
     sim.close()
     return info
 
@@ -433,7 +437,7 @@ def product_arm(args, rank, world, local_rank):
                            "reseed": f"state re-seeded (untimed, +{args.warmup} warm-up steps) every 8 timed steps (profiles/r1_stability.md)",
                            "l2": "working set ~4.7 GB per GPU per step >> 126 MB L2", "colours": "off",
                            "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
-                "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "sampled at N=1 only"},
+                "clocks": dict({k: info["clocks"].get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples", "power_w_max")}, note="GPU 0, sampled over the seed + timed segments"),
                 "e2e": {"value": info["P_global"] * info["e2e_steps"] / (info["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": info["h2d"],
                         "d2h_bytes_per_step": info["d2h"], "steps": info["e2e_steps"],
                         "what": "per rank and step: flip_upload_rows(s) H2D + sharded flip_step + flip_readback_particles(owned positions) D2H, pinned host buffers, host wall clock, max over ranks"},
