@@ -26,8 +26,8 @@ sys.path.insert(0, ROOT)
 METRIC = "flip_particle_steps_per_s"
 UNIT = "particle-steps/s"
 BENCH_N = 4096
-TRAFFIC_NCU = 196.4e6  # bytes per launch: dram__bytes_read.sum (145.2 MB) + dram__bytes_write.sum (51.2 MB) of sor_gs_tiled_kernel<1,1>,
-                       # ncu --set full, profiles/r1_final_ncu_flip_4096.md (temporal blocking: 154x below the algorithmic 30.2 GB)
+TRAFFIC_NCU = 197.5e6  # bytes per launch: dram__bytes_read.sum (144.9 MB) + dram__bytes_write.sum (52.6 MB) of sor_gs_tiled_kernel<1,1,16>,
+                       # ncu --set full, profiles/r1_final_ncu_flip_4096.md (temporal blocking: ~150x below the algorithmic 30.2 GB)
 WORKLOAD = "flip_fluid synthetic dam-break 4096^2 grid, 64264080 particles, 50 SOR iters, 2 separation sweeps (BASELINE configs[2])"
 
 
