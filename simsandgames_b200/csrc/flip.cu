@@ -2,14 +2,21 @@
 // Replaces struct FlipFluid (reference flip_fluid/src/flip_fluid.h:13-582); every kernel cites the
 // reference lines whose arithmetic it reproduces.  Compiled with -fmad=false: fp32 products and sums
 // stay unfused and in the reference's association order, so per-particle phases are bit-exact against
-// the serial CPU step and only summation ORDER (P2G) or sweep ORDER (separation, red-black) differ.
+// the serial CPU step and only the ORDER of some reductions differs in the production path (P2G adds,
+// separation sweep, rest-density sum) -- flip_set_exact_order() switches those to the reference's order too.
 //
-// Data layout in HBM (DESIGN.md "layout"):
+// One simulate() = integrate+histogram -> running sum, fill, per-cell fix-up, physical reorder (F1,F2)
+//   -> 2 Jacobi separation sweeps (F3) -> collide + mark + base-cell histogram (F4,F5)
+//   -> per-cell slot lists -> gather-form P2G + density + rest latch (F6,F7) -> SOR solve (F9, sor*.cu)
+//   -> G2P (F8) [-> colours (F10)].   The slab-sharded step (shard_step) wraps the same kernels.
+//
+// Data layout in HBM:
 //   grid   : u v prev_u prev_v p s density  float[C], cell_type int[C], x-fastest like fIX (flip_fluid.h:147)
 //   particles: pos/vel float2[P] x2 (ping-pong), physically sorted by spatial-hash cell (pIX order,
 //            descending caller id inside a cell -- exactly cell_particle_ids order, flip_fluid.h:196-197);
 //            orig[] = caller index of each slot == cell_particle_ids.
 //   hash   : num_cell_particles int[Hc], first_cell_particle int[Hc+1]  (bit-exact vs flip_fluid.h:169-198)
+//   P2G    : gcount int[C], gfirst int[C+1] + slot lists per stencil base cell (scratch reused from the sort)
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -1710,6 +1717,8 @@ int flip_upload_particles(FlipSim* f, const float* pos, const float* vel, const 
 	FG_CHECK(f && (n == 0 || (pos && ids)), FLIPGPU_EINVAL, "flip_upload_particles: null argument");
 	FG_CHECK(f->sharded, FLIPGPU_ESTATE, "flip_upload_particles is for sharded simulations");
 	FG_CHECK(n >= 0 && n <= f->d.max_particles, FLIPGPU_EINVAL, "flip_upload_particles: %d particles exceed the local capacity %d", n, f->d.max_particles);
+	for (int k = 0; k < n; k++)
+		FG_CHECK(ids[k] >= 0 && ids[k] < f->global_particles, FLIPGPU_EINVAL, "flip_upload_particles: id %d outside [0,%d)", ids[k], f->global_particles);
 	DeviceGuard guard(f->device);
 	const int c = f->cur;
 	if (n) {
