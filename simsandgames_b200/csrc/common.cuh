@@ -63,6 +63,8 @@ struct SorGrid {
 	const int* cell_type;  // only FLUID_CELL cells are updated (flip_fluid.h:462 / fluid.h:110)
 	const float* density;  // particle_density for the drift term, or nullptr
 	const float* rest;     // device scalar particle_rest_density, or nullptr
+	float *alt_f = nullptr, *alt_s = nullptr, *alt_p = nullptr;  // ping-pong partners of vel_f/vel_s/p for the tiled red-black
+	                       // kernel (optional; without them the one-launch-per-colour kernel runs)
 	bool x_fast;           // true: fast axis is x (FLIP); false: fast axis is y (Euler).  Fixes the fp32
 	                       // association order of the divergence (flip_fluid.h:476 / fluid.h:122-123)
 };
@@ -77,7 +79,12 @@ int sor_solve_strips(SorWorkspace** ws, const SorGrid& g, int iters, float cp, f
 // order: FlipSolverOrder.  s_binary: every s is 0 or 1 (required by the blocked kernel's 1-byte cell code;
 // otherwise LEX_WAVEFRONT falls back to the unblocked diagonal kernel, same results).
 int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,
-              cudaStream_t st, LaunchCounter* lc);
+              cudaStream_t st, LaunchCounter* lc, bool* swapped = nullptr);
+// temporally blocked red-black (sor_tiled.cu): cell constants once per solve, then rounds of up to 8 colour passes
+int sor_rb_prep(SorWorkspace** ws, const SorGrid& g, bool drift, int row_lo, int row_hi, cudaStream_t st, LaunchCounter* lc);
+int sor_rb_round(SorWorkspace* w, const SorGrid& g, float* out_f, float* out_s, float* out_p, int passes, int colour0, int row_lo,
+                 int row_hi, float cp, float omega, bool drift, cudaStream_t st, LaunchCounter* lc);
+int sor_rb_passes_per_round();
 void sor_rb_rows_launch(const SorGrid& g, int colour, int shift, int lo, int hi, float cp, float omega, bool drift, cudaStream_t st);
 int sor_residual(const SorGrid& g, bool drift, float* d_partials, int n_partials, float* h_out2, cudaStream_t st,
                  LaunchCounter* lc);

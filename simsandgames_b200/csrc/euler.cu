@@ -118,6 +118,7 @@ struct EulerSim {
 	cudaStream_t st = nullptr;
 	float *u = nullptr, *v = nullptr, *new_u = nullptr, *new_v = nullptr, *pressure = nullptr, *m = nullptr, *new_m = nullptr;
 	unsigned char* solid = nullptr;
+	float *u_alt = nullptr, *v_alt = nullptr, *p_alt = nullptr;  // ping-pong partners for the tiled red-black projection (lazy)
 	float* s = nullptr;        // derived: !solid
 	int* cell_type = nullptr;  // derived
 	bool coeff_dirty = true;
@@ -151,6 +152,7 @@ SorGrid esor(EulerSim* e) {
 	g.nf = e->d.num_y; g.ns = e->d.num_x;
 	g.vel_f = e->v; g.vel_s = e->u; g.p = e->pressure; g.s = e->s; g.cell_type = e->cell_type;
 	g.density = nullptr; g.rest = nullptr; g.x_fast = false;
+	g.alt_f = e->v_alt; g.alt_s = e->u_alt; g.alt_p = e->p_alt;
 	return g;
 }
 float** efield(EulerSim* e, int field) {
@@ -165,7 +167,14 @@ int project(EulerSim* e, int iters, float dt, int order) {
 	FG_TRY(refresh_coeff(e));
 	FG_CUDA(cudaMemsetAsync(e->pressure, 0, (size_t)e->d.num_cells * 4, e->st));  // fluid.h:101-103
 	float cp = e->d.density * e->d.h / dt;                                          // fluid.h:100
-	return sor_solve(&e->ws, esor(e), iters, cp, 1.9f, false, order, true, e->st, &e->lc);
+	if (order == FLIP_SOLVER_RED_BLACK && !e->u_alt) {
+		size_t C = e->d.num_cells;
+		FG_CUDA(cudaMalloc(&e->u_alt, C * 4)); FG_CUDA(cudaMalloc(&e->v_alt, C * 4)); FG_CUDA(cudaMalloc(&e->p_alt, C * 4));
+	}
+	bool swapped = false;
+	FG_TRY(sor_solve(&e->ws, esor(e), iters, cp, 1.9f, false, order, true, e->st, &e->lc, &swapped));
+	if (swapped) { std::swap(e->u, e->u_alt); std::swap(e->v, e->v_alt); std::swap(e->pressure, e->p_alt); }
+	return FLIPGPU_OK;
 }
 int extrapolate(EulerSim* e) {
 	EGeo g = egeo(e);
@@ -235,7 +244,7 @@ int euler_destroy(EulerSim* e) {
 	if (!e) return FLIPGPU_OK;
 	EDeviceGuard guard(e->device);
 	cudaStreamSynchronize(e->st);
-	void* ptrs[] = {e->u, e->v, e->new_u, e->new_v, e->pressure, e->m, e->new_m, e->s, e->solid, e->cell_type, e->d_partials};
+	void* ptrs[] = {e->u, e->v, e->new_u, e->new_v, e->pressure, e->m, e->new_m, e->s, e->solid, e->cell_type, e->d_partials, e->u_alt, e->v_alt, e->p_alt};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	sor_workspace_free(e->ws);
 	cudaStreamDestroy(e->st);

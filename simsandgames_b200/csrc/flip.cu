@@ -865,6 +865,7 @@ struct FlipSim {
 	int device = 0;
 	cudaStream_t st = nullptr;
 	float *u = nullptr, *v = nullptr, *prev_u = nullptr, *prev_v = nullptr, *p = nullptr, *s = nullptr, *dens = nullptr;
+	float *u_alt = nullptr, *v_alt = nullptr, *p_alt = nullptr;  // ping-pong partners for the tiled red-black solve (lazy)
 	int* cell_type = nullptr;
 	float* cell_color = nullptr;  // lazily allocated
 	float2* pos[2] = {nullptr, nullptr};
@@ -1173,7 +1174,23 @@ SorGrid sor_view(FlipSim* f) {
 	g.nf = f->d.f_num_x; g.ns = f->d.f_num_y;
 	g.vel_f = f->u; g.vel_s = f->v; g.p = f->p; g.s = f->s; g.cell_type = f->cell_type;
 	g.density = f->dens; g.rest = f->d_rest; g.x_fast = true;
+	g.alt_f = f->u_alt; g.alt_s = f->v_alt; g.alt_p = f->p_alt;
 	return g;
+}
+int ensure_alt(FlipSim* f) {
+	if (f->u_alt) return FLIPGPU_OK;
+	size_t C = f->d.f_num_cells;
+	FG_CUDA(cudaMalloc(&f->u_alt, C * 4)); FG_CUDA(cudaMalloc(&f->v_alt, C * 4)); FG_CUDA(cudaMalloc(&f->p_alt, C * 4));
+	FG_CUDA(cudaMemsetAsync(f->u_alt, 0, C * 4, f->st)); FG_CUDA(cudaMemsetAsync(f->v_alt, 0, C * 4, f->st)); FG_CUDA(cudaMemsetAsync(f->p_alt, 0, C * 4, f->st));
+	return FLIPGPU_OK;
+}
+// the projection of one step; an odd number of ping-pong rounds leaves the result in the partner arrays -> swap the names
+int solve(FlipSim* f, int iters, float cp, float omega, bool drift, int order) {
+	if (order == FLIP_SOLVER_RED_BLACK && f->s_binary) FG_TRY(ensure_alt(f));
+	bool swapped = false;
+	FG_TRY(sor_solve(&f->ws, sor_view(f), iters, cp, omega, drift, order, f->s_binary, f->st, &f->lc, &swapped));
+	if (swapped) { std::swap(f->u, f->u_alt); std::swap(f->v, f->v_alt); std::swap(f->p, f->p_alt); }
+	return FLIPGPU_OK;
 }
 
 int g2p(FlipSim* f, float flip_ratio) {
@@ -1293,11 +1310,26 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 	return FLIPGPU_OK;
 }
 
-// red-black sweeps with the communication-avoiding deep halo of sor_shard.cu, on this handle's (global-size) arrays
+// red-black sweeps with the communication-avoiding deep halo of sor_shard.cu, on this handle's (global-size) arrays.
+// With 0/1-valued s every exchange is followed by ONE temporally blocked launch that runs the 8 colour passes the 9-row
+// halo allows (sor_rb_tiled_kernel); otherwise one launch per colour pass on the shrinking row band.
 int shard_solve(FlipSim* f, int iters, float cp, float omega, bool drift) {
-	SorGrid g = sor_view(f);
-	const int H = f->halo, K = std::max(H - 1, 1);
+	const int H = f->halo, K = std::max(H - 1, 1), ny = f->d.f_num_y;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
+	if (f->s_binary && K == sor_rb_passes_per_round()) {
+		FG_TRY(ensure_alt(f));
+		FG_TRY(sor_rb_prep(&f->ws, sor_view(f), drift, f->gy0, f->gy1, f->st, &f->lc));
+		const int out_lo = has_down ? f->j0 - 1 : f->j0, out_hi = has_up ? f->j1 + 1 : f->j1;   // own rows +- 1: completes the shared face rows
+		for (int pass0 = 0; pass0 < 2 * iters; pass0 += K) {
+			void* vel[2] = {f->u, f->v};
+			FG_TRY(shard_exchange_rows(f, vel, 2, H));
+			FG_TRY(sor_rb_round(f->ws, sor_view(f), f->u_alt, f->v_alt, f->p_alt, std::min(K, 2 * iters - pass0), pass0 & 1, std::max(out_lo, 0),
+			                    std::min(out_hi, ny), cp, omega, drift, f->st, &f->lc));
+			std::swap(f->u, f->u_alt); std::swap(f->v, f->v_alt); std::swap(f->p, f->p_alt);
+		}
+		return FLIPGPU_OK;
+	}
+	SorGrid g = sor_view(f);
 	void* vel[2] = {f->u, f->v};
 	int pass = 0;
 	for (int it = 0; it < iters; it++)
@@ -1305,7 +1337,7 @@ int shard_solve(FlipSim* f, int iters, float cp, float omega, bool drift) {
 			const int m = f->nranks > 1 ? pass % K : 0;
 			if (f->nranks > 1 && m == 0) FG_TRY(shard_exchange_rows(f, vel, 2, H));
 			int lo = has_down ? f->j0 - (H - 1) + m : f->j0, hi = has_up ? f->j1 + (H - 1) - m - 1 : f->j1 - 1;
-			lo = std::max(lo, 1); hi = std::min(hi, f->d.f_num_y - 2);
+			lo = std::max(lo, 1); hi = std::min(hi, ny - 2);
 			if (hi < lo) continue;
 			sor_rb_rows_launch(g, colour, 0, lo, hi, cp, omega, drift && g.density && g.rest, f->st);
 			f->lc.n++;
@@ -1476,7 +1508,7 @@ int flip_destroy(FlipSim* f) {
 	DeviceGuard guard(f->device);
 	cudaStreamSynchronize(f->st);
 	void* ptrs[] = {f->u, f->v, f->prev_u, f->prev_v, f->p, f->s, f->dens, f->cell_type, f->cell_color, f->pos[0], f->pos[1],
-	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->gcount, f->gfirst, f->count,
+	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->gcount, f->gfirst, f->count, f->u_alt, f->v_alt, f->p_alt,
 	                f->first, f->tile_sum, f->d_rest, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (f->comm) g_nccl.CommDestroy(f->comm);
@@ -1649,8 +1681,7 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		phase_mark(f, FLIP_PH_P2G);
 		FG_TRY(p2g(f));
 		phase_mark(f, FLIP_PH_SOLVE);
-		FG_TRY(sor_solve(&f->ws, sor_view(f), sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0,
-		                 sp->solver_order, f->s_binary, f->st, &f->lc));
+		FG_TRY(solve(f, sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0, sp->solver_order));
 		phase_mark(f, FLIP_PH_G2P);
 		FG_TRY(g2p(f, sp->flip_ratio));
 		phase_mark(f, FLIP_PH_COLORS);
@@ -1813,7 +1844,7 @@ int flip_phase_solve(FlipSim* f, int iters, float dt, float omega, int drift, in
 	FG_CUDA(cudaMemsetAsync(f->p, 0, (size_t)f->d.f_num_cells * 4, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->prev_u, f->u, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->prev_v, f->v, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
-	return sor_solve(&f->ws, sor_view(f), iters, f->d.density * f->d.h / dt, omega, drift != 0, order, f->s_binary, f->st, &f->lc);
+	return solve(f, iters, f->d.density * f->d.h / dt, omega, drift != 0, order);
 }
 int flip_phase_g2p(FlipSim* f, float flip_ratio) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");

@@ -12,6 +12,7 @@
 //     -> bit-identical u,v,p (this file is compiled with -fmad=false);
 //   * RED_BLACK: cells with (i+j) even, then odd: the performance order named by north_star.
 #include <cooperative_groups.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(256) sor_wavefront_kernel(SorGrid g, int iters
 }
 
 int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,
-              cudaStream_t st, LaunchCounter* lc) {
+              cudaStream_t st, LaunchCounter* lc, bool* swapped) {
+	if (swapped) *swapped = false;
 	if (iters <= 0 || g.nf < 3 || g.ns < 3) return FLIPGPU_OK;
 	bool use_drift = drift && g.density && g.rest;
 	if (order == FLIP_SOLVER_LEX_WAVEFRONT && s_binary && ws) return sor_solve_tiled(ws, g, iters, cp, omega, drift, st, lc);
@@ -106,6 +108,19 @@ int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float om
 		return FLIPGPU_OK;
 	}
 	FG_CHECK(order == FLIP_SOLVER_RED_BLACK, FLIPGPU_EINVAL, "unknown solver order %d", order);
+	if (s_binary && ws && swapped && g.alt_f && g.alt_s && g.alt_p) {
+		// temporally blocked: 8 colour passes per launch, ping-pong between the arrays and their partners
+		FG_TRY(sor_rb_prep(ws, g, drift, 0, g.ns, st, lc));
+		SorGrid cur = g;
+		float *of = g.alt_f, *os = g.alt_s, *op = g.alt_p;
+		const int K = sor_rb_passes_per_round();
+		for (int pass0 = 0; pass0 < 2 * iters; pass0 += K) {
+			FG_TRY(sor_rb_round(*ws, cur, of, os, op, std::min(K, 2 * iters - pass0), pass0 & 1, 0, g.ns, cp, omega, drift, st, lc));
+			std::swap(cur.vel_f, of); std::swap(cur.vel_s, os); std::swap(cur.p, op);
+			*swapped = !*swapped;
+		}
+		return FLIPGPU_OK;
+	}
 	dim3 block(64, 4);
 	dim3 grid(cdiv((size_t)(g.nf + 1) / 2 + 1, block.x), cdiv((size_t)g.ns - 2, block.y));
 	for (int it = 0; it < iters; it++)

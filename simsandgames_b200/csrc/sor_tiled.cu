@@ -205,10 +205,10 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 
 // per-solve constants of every cell: the neighbour-openness code and the drift term
 __global__ void __launch_bounds__(256) sor_prep_kernel(SorGrid g, bool drift, unsigned char* __restrict__ code,
-                                                       float* __restrict__ drift_out, unsigned char* __restrict__ act, int na) {
+                                                       float* __restrict__ drift_out, unsigned char* __restrict__ act, int na,
+                                                       size_t c_begin, size_t c_end) {
 	float rest = (drift && g.rest) ? *g.rest : 0.f;
-	size_t n = (size_t)g.nf * g.ns;
-	for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+	for (size_t c = c_begin + blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < c_end; c += (size_t)gridDim.x * blockDim.x) {
 		int a = (int)(c % g.nf), b = (int)(c / g.nf);
 		unsigned cd = 0;
 		float dr = 0.f;
@@ -258,7 +258,7 @@ void sor_workspace_free(SorWorkspace* w) {
 	delete w;
 }
 
-static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
+static int ensure_cell_constants(SorWorkspace* w, const SorGrid& g) {
 	if (w->nf != g.nf || w->ns != g.ns) {
 		cudaFree(w->code); cudaFree(w->drift);
 		w->code = nullptr; w->drift = nullptr;
@@ -278,6 +278,11 @@ static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
 		FG_CUDA(cudaGetDevice(&dev));
 		FG_CUDA(cudaDeviceGetAttribute(&w->sms, cudaDevAttrMultiProcessorCount, dev));
 	}
+	return FLIPGPU_OK;
+}
+
+static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
+	FG_TRY(ensure_cell_constants(w, g));
 	if (w->iters != iters) {
 		int maxc = kMaxChunk;
 		if (const char* e = getenv("FLIPGPU_SOR_KC")) maxc = std::max(1, std::min(kMaxChunk, atoi(e)));  // tuning knob
@@ -330,7 +335,7 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	FG_TRY(plan(w, g, iters, st));
 	bool use_drift = drift && g.density && g.rest;
 	FG_CUDA(cudaMemsetAsync(w->act, 0, (size_t)w->na * w->nb, st));
-	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, w->act, w->na);
+	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, w->act, w->na, 0, (size_t)g.nf * g.ns);
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
 	w->epoch++;
 	TiledArgs A;
@@ -359,6 +364,150 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	return FLIPGPU_OK;
 }
 
+
+// ===================================================================================================
+// Temporally blocked RED-BLACK SOR (north_star: "red-black SOR pressure solve ... staged through shared memory").
+// A CTA stages a (T+2K+1)^2 box of u, v, p, the cell code and the drift term in shared memory, runs K colour passes on
+// it -- the region whose inputs are still exact shrinks by one cell per pass on every side -- and writes the exact T x T
+// interior to the OUTPUT arrays (ping-pong: a neighbouring tile may still be reading this tile's cells as its halo).
+// Halo cells are recomputed by every tile that needs them, with identical arithmetic on identical inputs, so the
+// result is bit-identical to one launch per colour (sor_rb_pass_kernel) at 1/K of the HBM sweeps; K = 8 passes also
+// matches the 9-row deep halo of the slab-sharded solve (one NCCL exchange per launch).
+constexpr int kRbT = 64, kRbK = 8, kRbW = kRbT + 2 * kRbK + 1;
+// Box rows are stored de-interleaved by column parity (even columns first, then odd): the cells of one colour in a
+// row, their x+1 neighbours and their y+1 neighbours are then each contiguous in shared memory -- no bank conflicts.
+constexpr int kRbWh = (kRbW + 1) / 2, kRbRow = 2 * kRbWh, kRbBox = kRbRow * kRbW;
+__device__ __forceinline__ int rb_index(int lx, int ly) { return ly * kRbRow + (lx & 1) * kRbWh + (lx >> 1); }
+
+struct RbArgs {
+	int nf, ns;
+	const float *in_f, *in_s, *in_p;
+	float *out_f, *out_s, *out_p;
+	const unsigned char* code;
+	const float* drift;
+	int row_lo, row_hi;  // output rows [row_lo, row_hi)
+	int passes, colour0; // colour passes in this launch (<= K) and the colour of the first one
+	int tiles_x;
+	float cp, omega;
+};
+
+template <bool XFAST, bool DRIFT>
+__global__ void __launch_bounds__(512, 2) sor_rb_tiled_kernel(RbArgs A) {
+	extern __shared__ float smem_rb[];
+	float* s_f = smem_rb;
+	float* s_s = s_f + kRbBox;
+	float* s_p = s_s + kRbBox;
+	float* s_d = s_p + kRbBox;  // only touched when DRIFT
+	unsigned char* s_c = reinterpret_cast<unsigned char*>(s_d + (DRIFT ? kRbBox : 0));
+	const int tid = threadIdx.y * 32 + threadIdx.x;
+	const int X0 = (blockIdx.x % A.tiles_x) * kRbT, Y0 = A.row_lo + (blockIdx.x / A.tiles_x) * kRbT;
+	const int BX = X0 - kRbK, BY = Y0 - kRbK;
+	// stage the box: batches of 4 elements per thread with all loads of a batch in flight before any is stored
+	for (int e0 = tid; e0 < kRbW * kRbW; e0 += 4 * 512) {
+		float vf[4], vs[4], pp[4], dr[4];
+		unsigned char cd[4];
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			int e = e0 + r * 512;
+			int lx = e % kRbW, ly = e / kRbW;
+			int F = BX + lx, S = BY + ly;
+			vf[r] = 0.f; vs[r] = 0.f; pp[r] = 0.f; dr[r] = 0.f; cd[r] = 0;
+			if (e < kRbW * kRbW && F >= 0 && F < A.nf && S >= 0 && S < A.ns) {
+				size_t c = (size_t)F + (size_t)A.nf * S;
+				vf[r] = A.in_f[c]; vs[r] = A.in_s[c]; pp[r] = A.in_p[c]; cd[r] = A.code[c];
+				if (DRIFT) dr[r] = A.drift[c];
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			int e = e0 + r * 512;
+			if (e < kRbW * kRbW) {
+				int b = rb_index(e % kRbW, e / kRbW);
+				s_f[b] = vf[r]; s_s[b] = vs[r]; s_p[b] = pp[r]; s_c[b] = cd[r];
+				if (DRIFT) s_d[b] = dr[r];
+			}
+		}
+	}
+	__syncthreads();
+	for (int m = 0; m < A.passes; m++) {
+		const int colour = (A.colour0 + m) & 1, hi = kRbW - 2 - m;
+		// a thread's rows are 16 apart, so they share the parity: its columns and box offsets are fixed for the pass and the
+		// row loop only adds a constant
+		const int ly0 = m + threadIdx.y;
+		const int lxa = m + ((BX + m + BY + ly0 + colour) & 1) + 2 * threadIdx.x;
+#pragma unroll
+		for (int half = 0; half < 2; half++) {
+			const int lx = lxa + 64 * half;
+			if (lx > hi) break;
+			int e = rb_index(lx, ly0), ex = rb_index(lx + 1, ly0);
+			for (int ly = ly0; ly <= hi; ly += 16, e += 16 * kRbRow, ex += 16 * kRbRow) {
+				const int ey = e + kRbRow;
+				const unsigned cd = s_c[e];
+				if (!(cd & 1u)) continue;  // code 0 outside the grid interior, on solid/air cells and where s_sum == 0
+				float vfc = s_f[e], vfp = s_f[ex], vsc = s_s[e], vsp = s_s[ey];
+				float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
+				if (DRIFT) div -= s_d[e];
+				if (cd == 31u) {
+					float pv = (-div * 0.25f) * A.omega;
+					s_p[e] += A.cp * pv;
+					s_f[e] = vfc - pv; s_f[ex] = vfp + pv; s_s[e] = vsc - pv; s_s[ey] = vsp + pv;
+				} else {
+					float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
+					float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
+					float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+					float pv = -div / ssum;
+					pv *= A.omega;
+					s_p[e] += A.cp * pv;
+					s_f[e] = vfc - sfm * pv; s_f[ex] = vfp + sfp * pv;
+					s_s[e] = vsc - ssm * pv; s_s[ey] = vsp + ssp * pv;
+				}
+			}
+		}
+		__syncthreads();
+	}
+	for (int e = tid; e < kRbT * kRbT; e += 512) {
+		int ix = e % kRbT, iy = e / kRbT;
+		int F = X0 + ix, S = Y0 + iy;
+		if (F >= A.nf || S >= A.row_hi) continue;
+		int b = rb_index(ix + kRbK, iy + kRbK);
+		size_t c = (size_t)F + (size_t)A.nf * S;
+		A.out_f[c] = s_f[b]; A.out_s[c] = s_s[b]; A.out_p[c] = s_p[b];
+	}
+}
+
+// per-solve cell constants (code, drift) for the temporally blocked red-black kernel
+int sor_rb_prep(SorWorkspace** wsp, const SorGrid& g, bool drift, int row_lo, int row_hi, cudaStream_t st, LaunchCounter* lc) {
+	if (!*wsp) *wsp = new SorWorkspace;
+	SorWorkspace* w = *wsp;
+	FG_TRY(ensure_cell_constants(w, g));
+	bool use_drift = drift && g.density && g.rest;
+	const size_t c0 = (size_t)g.nf * std::max(row_lo, 0), c1 = (size_t)g.nf * std::min(row_hi, g.ns);
+	sor_prep_kernel<<<wave_grid(c1 - c0, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, nullptr, 0, c0, c1);
+	if (lc) lc->n++;
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
+// `passes` (<= 8) colour passes, first colour = colour0, reading g's arrays and writing rows [row_lo,row_hi) of the out arrays
+int sor_rb_round(SorWorkspace* w, const SorGrid& g, float* out_f, float* out_s, float* out_p, int passes, int colour0, int row_lo,
+                 int row_hi, float cp, float omega, bool drift, cudaStream_t st, LaunchCounter* lc) {
+	if (row_hi <= row_lo || passes <= 0) return FLIPGPU_OK;
+	bool use_drift = drift && g.density && g.rest;
+	RbArgs A;
+	A.nf = g.nf; A.ns = g.ns; A.in_f = g.vel_f; A.in_s = g.vel_s; A.in_p = g.p; A.out_f = out_f; A.out_s = out_s; A.out_p = out_p;
+	A.code = w->code; A.drift = use_drift ? w->drift : nullptr; A.row_lo = row_lo; A.row_hi = row_hi;
+	A.passes = std::min(passes, kRbK); A.colour0 = colour0 & 1; A.tiles_x = (g.nf + kRbT - 1) / kRbT; A.cp = cp; A.omega = omega;
+	const int tiles_y = (row_hi - row_lo + kRbT - 1) / kRbT;
+	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_rb_tiled_kernel<true, true> : (const void*)sor_rb_tiled_kernel<true, false>)
+	                          : (use_drift ? (const void*)sor_rb_tiled_kernel<false, true> : (const void*)sor_rb_tiled_kernel<false, false>);
+	const size_t smem = (size_t)kRbBox * ((use_drift ? 4 : 3) * sizeof(float) + 1);
+	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	void* args[] = {&A};
+	FG_CUDA(cudaLaunchKernel(fn, dim3(A.tiles_x * tiles_y), dim3(32, 16), args, smem, st));
+	if (lc) lc->n++;
+	return FLIPGPU_OK;
+}
+int sor_rb_passes_per_round() { return kRbK; }
 
 // ===================================================================================================
 // Streaming-strip variant of the blocked wavefront (same order, same bits; the default).
@@ -575,7 +724,7 @@ int sor_solve_strips(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, 
 	SorWorkspace* w = *wsp;
 	FG_TRY(plan(w, g, iters, st));
 	bool use_drift = drift && g.density && g.rest;
-	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, nullptr, 0);
+	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, nullptr, 0, 0, (size_t)g.nf * g.ns);
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
 	FG_CUDA(cudaMemsetAsync(w->progress, 0, (size_t)w->ni * w->nq * 4, st));
 	StripArgs A;
