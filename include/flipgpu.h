@@ -174,6 +174,10 @@ int euler_advect_vel(EulerSim* sim, float dt);                     /* fluid.h:21
 int euler_advect_smoke(EulerSim* sim, float dt);                   /* fluid.h:241-259 */
 /* n_steps x (project, extrapolate, advectVel, advectSmoke) = eulerian_fluid/src/fluid_ui.h:107-111 */
 int euler_step(EulerSim* sim, int iters, float dt, int order, int n_steps);
+/* device FluidUI::setObstacle, eulerian_fluid/src/fluid_ui.h:24-62: clears `solid`, rebuilds the left/top/bottom walls and
+ * a solid disc of radius r cells centred on cell (x, y) whose cells get m = 1, u = vx, v = vy.  The caller supplies
+ * (vx, vy) = (x - previous x, y - previous y) / dt as :39-43 does when reset == false, else 0. */
+int euler_set_obstacle(EulerSim* sim, int x, int y, int r, float vx, float vy);
 /* sampleField fluid.h:153-188 at n query points (field: 0 U, 1 V, 2 S) */
 int euler_sample_field(EulerSim* sim, int field, const float* xs, const float* ys, float* out, size_t n);
 int euler_get_residual(EulerSim* sim, float* max_div, float* rms_div);

@@ -218,6 +218,12 @@ class EulerOracle:
         fn = self._fn("sample"); fn.restype = C.c_float; fn.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int]
         return fn(self.h_, x, y, field)
 
+    def set_obstacle(self, x, y, r, vx=0.0, vy=0.0):
+        """FluidUI::setObstacle (fluid_ui.h:24-62): walls + solid disc carrying velocity (vx, vy)."""
+        fn = self._fn("set_obstacle")
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        fn(self.h_, int(x), int(y), int(r), vx, vy)
+
     def step(self, iters, dt, n_steps=1, timed=False):
         """solve -> extrapolate -> advectVel -> advectSmoke (fluid_ui.h:107-111)."""
         fn = self._fn("step"); fn.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double)]
@@ -308,8 +314,9 @@ def make_flip_scene(kind="default", N=None, oracle_kind=None, with_obstacle=None
     return o, params, geom
 
 
-def euler_set_obstacle(o, x, y, r):
-    """eulerian_fluid/src/fluid_ui.h:25-62 with reset=true (integer disc, left/top/bottom walls)."""
+def euler_set_obstacle(o, x, y, r, vx=0.0, vy=0.0):
+    """numpy restatement of eulerian_fluid/src/fluid_ui.h:25-62 (integer disc, left/top/bottom walls); the C
+    restatements are EulerOracle.set_obstacle, cross-checked against this one in tests/test_oracle_pin.py."""
     o.solid[:] = 0
     o.solid[0, :] = 1
     o.solid[:, 0] = 1
@@ -320,8 +327,8 @@ def euler_set_obstacle(o, x, y, r):
     disc[0, :] = False; disc[-1, :] = False; disc[:, 0] = False; disc[:, -1] = False
     o.solid[disc] = 1
     o.m[disc] = 1.0
-    o.u[disc] = 0.0
-    o.v[disc] = 0.0
+    o.u[disc] = vx
+    o.v[disc] = vy
 
 
 def make_euler_scene(x=96, y=72, oracle_kind=None):

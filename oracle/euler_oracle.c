@@ -160,6 +160,32 @@ void orceuler_advect_smoke(void* h, float dt) {
 	memcpy(f->m, f->new_m, bytes);
 }
 
+/* FluidUI::setObstacle, eulerian_fluid/src/fluid_ui.h:24-62.  The UI shell owns this function (it is not a member of
+ * class Fluid and its header needs the windowing engine, so it cannot be compiled into oracle/_ref): parity for it is
+ * anchored on this restatement + the independent numpy one in tests/.  (vx, vy) = (x - previous x) / dt when the
+ * caller passes reset = false (:39-43), else 0.  int arithmetic like the reference ("int is used for overflow reasons"). */
+void orceuler_set_obstacle(void* h, int x, int y, int r, float vx, float vy) {
+	Euler* f = (Euler*)h;
+	memset(f->solid, 0, (size_t)f->ncells);                       /* :25 */
+	for (int j = 0; j < f->ny; j++) f->solid[IX(0, j)] = 1;       /* left wall :28-30 */
+	for (int i = 0; i < f->nx; i++) {                             /* top, bottom :33-36 */
+		f->solid[IX(i, 0)] = 1;
+		f->solid[IX(i, f->ny - 1)] = 1;
+	}
+	for (int i = 1; i < f->nx - 1; i++) {                         /* disc :49-60 */
+		int dx = i - x;
+		for (int j = 1; j < f->ny - 1; j++) {
+			int dy = j - y;
+			if (dx * dx + dy * dy < r * r) {
+				f->solid[IX(i, j)] = 1;
+				f->m[IX(i, j)] = 1.f;
+				f->u[IX(i, j)] = vx;
+				f->v[IX(i, j)] = vy;
+			}
+		}
+	}
+}
+
 /* caller sequence, eulerian_fluid/src/fluid_ui.h:107-111 */
 void orceuler_step(void* h, int iters, float dt, int n_steps, double* phase_ns) {
 	for (int k = 0; k < n_steps; k++) {

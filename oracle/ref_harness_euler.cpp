@@ -38,6 +38,24 @@ void refeuler_extrapolate(void* h) { ((Fluid*)h)->extrapolate(); }
 void refeuler_advect_vel(void* h, float dt) { ((Fluid*)h)->advectVel(dt); }
 void refeuler_advect_smoke(void* h, float dt) { ((Fluid*)h)->advectSmoke(dt); }
 float refeuler_sample(void* h, float x, float y, int field) { return ((Fluid*)h)->sampleField(x, y, field); }
+// FluidUI::setObstacle (eulerian_fluid/src/fluid_ui.h:24-62) lives in the UI shell, whose header needs the windowing
+// engine; this is the harness's restatement of it acting on the reference object's public arrays, so that scenes with
+// a dragged obstacle can be driven through the reference solver.  (vx, vy) = (x - previous x)/dt or 0 (:39-43).
+void refeuler_set_obstacle(void* h, int x, int y, int r, float vx, float vy) {
+	Fluid* f = (Fluid*)h;
+	const int nx = f->getNumX(), ny = f->getNumY();
+	std::memset(f->solid, false, sizeof(bool) * nx * ny);
+	for (int j = 0; j < ny; j++) f->solid[f->ix(0, j)] = true;
+	for (int i = 0; i < nx; i++) { f->solid[f->ix(i, 0)] = true; f->solid[f->ix(i, ny - 1)] = true; }
+	for (int i = 1; i < nx - 1; i++)
+		for (int j = 1; j < ny - 1; j++) {
+			int dx = i - x, dy = j - y;
+			if (dx * dx + dy * dy < r * r) {
+				int c = f->ix(i, j);
+				f->solid[c] = true; f->m[c] = 1.f; f->u[c] = vx; f->v[c] = vy;
+			}
+		}
+}
 // caller sequence of eulerian_fluid/src/fluid_ui.h:107-111
 void refeuler_step(void* h, int iters, float dt, int n_steps, double* phase_ns) {
 	Fluid* f = (Fluid*)h;

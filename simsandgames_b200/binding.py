@@ -288,6 +288,7 @@ class FluidGPU:
         _check(self._lib.euler_get_dims(self._h, C.byref(d)), "euler_get_dims")
         self._num_x, self._num_y, self._num_cells = d.num_x, d.num_y, d.num_cells
         self.density, self.h, self.h1 = np.float32(d.density), np.float32(d.h), np.float32(d.h1)
+        self.obstacle_x = self.obstacle_y = 0  # FluidUI's members, fluid_ui.h:17-18
 
     def getNumX(self):
         return self._num_x
@@ -335,6 +336,15 @@ class FluidGPU:
     def step(self, num_iter, dt, n_steps=1, solver_order=LEX_WAVEFRONT):
         """the caller sequence of eulerian_fluid/src/fluid_ui.h:107-111"""
         _check(self._lib.euler_step(self._h, int(num_iter), C.c_float(dt), int(solver_order), int(n_steps)), "euler_step")
+
+    def setObstacle(self, x, y, r, reset=True, dt=1.0):
+        """FluidUI::setObstacle(x, y, r, reset, dt) -- eulerian_fluid/src/fluid_ui.h:24-62 -- on the device."""
+        vx = vy = np.float32(0)
+        if not reset:  # :39-43, velocity = displacement of the obstacle since the previous call
+            vx = np.float32(int(x) - self.obstacle_x) / np.float32(dt)
+            vy = np.float32(int(y) - self.obstacle_y) / np.float32(dt)
+        self.obstacle_x, self.obstacle_y = int(x), int(y)
+        _check(self._lib.euler_set_obstacle(self._h, int(x), int(y), int(r), C.c_float(vx), C.c_float(vy)), "euler_set_obstacle")
 
     def sampleField(self, xs, ys, field):
         xs = np.ascontiguousarray(xs, np.float32).reshape(-1)

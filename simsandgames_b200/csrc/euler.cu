@@ -92,6 +92,29 @@ __global__ void k_extrapolate(EGeo g, float* __restrict__ u, float* __restrict__
 	}
 }
 
+// FluidUI::setObstacle, eulerian_fluid/src/fluid_ui.h:24-62: clear `solid`, left/top/bottom walls, then a solid disc
+// that carries (vx, vy) and resets its smoke to 1.  One thread per cell instead of memset + three loops; the disc test
+// is the reference's int arithmetic (dx*dx + dy*dy < r*r).
+__global__ void __launch_bounds__(256) k_euler_obstacle(EGeo g, int ox, int oy, int r, float vx, float vy,
+                                                        unsigned char* __restrict__ solid, float* __restrict__ m,
+                                                        float* __restrict__ u, float* __restrict__ v) {
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	int i = blockIdx.y * blockDim.y + threadIdx.y;
+	if (i >= g.nx || j >= g.ny) return;
+	int c = EIX(i, j);
+	bool sd = i == 0 || j == 0 || j == g.ny - 1;
+	if (i >= 1 && i < g.nx - 1 && j >= 1 && j < g.ny - 1) {
+		int dx = i - ox, dy = j - oy;
+		if (dx * dx + dy * dy < r * r) {
+			sd = true;
+			m[c] = 1.f;
+			u[c] = vx;
+			v[c] = vy;
+		}
+	}
+	solid[c] = sd ? 1 : 0;
+}
+
 __global__ void k_solid_to_coeff(int n, const unsigned char* __restrict__ solid, float* __restrict__ s, int* __restrict__ cell_type) {
 	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
 		bool sd = solid[c] != 0;
@@ -313,6 +336,19 @@ int euler_step(EulerSim* e, int iters, float dt, int order, int n_steps) {
 		FG_TRY(advect_vel(e, dt));
 		FG_TRY(advect_smoke(e, dt));
 	}
+	return FLIPGPU_OK;
+}
+
+int euler_set_obstacle(EulerSim* e, int x, int y, int r, float vx, float vy) {
+	FG_CHECK(e, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(r >= 0 && r < 46341, FLIPGPU_EINVAL, "euler_set_obstacle: radius %d", r);
+	EDeviceGuard guard(e->device);
+	EGeo g = egeo(e);
+	dim3 block(64, 4), grid(cdiv(g.ny, 64), cdiv(g.nx, 4));
+	k_euler_obstacle<<<grid, block, 0, e->st>>>(g, x, y, r, vx, vy, e->solid, e->m, e->u, e->v);
+	e->lc.n++;
+	FG_CUDA(cudaGetLastError());
+	e->coeff_dirty = true;
 	return FLIPGPU_OK;
 }
 

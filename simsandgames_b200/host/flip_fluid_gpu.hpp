@@ -149,6 +149,16 @@ struct FluidGPU {
 	void extrapolate() { push(); check(euler_extrapolate(sim_), "euler_extrapolate"); }
 	void advectVel(float dt) { push(); check(euler_advect_vel(sim_, dt), "euler_advect_vel"); }
 	void advectSmoke(float dt) { push(); check(euler_advect_smoke(sim_, dt), "euler_advect_smoke"); }
+	// device FluidUI::setObstacle(x, y, r, reset, dt), fluid_ui.h:24-62; the host mirrors of solid/m/u/v are NOT
+	// refreshed (call pull_velocity()/pull_render_state() or download what you need)
+	int obstacle_x = 0, obstacle_y = 0;
+	void setObstacle(int x, int y, int r, bool reset = true, float dt = 1) {
+		push();
+		float vx = 0.f, vy = 0.f;
+		if (!reset) { vx = (x - obstacle_x) / dt; vy = (y - obstacle_y) / dt; }
+		obstacle_x = x; obstacle_y = y;
+		check(euler_set_obstacle(sim_, x, y, r, vx, vy), "euler_set_obstacle");
+	}
 	void pull_render_state() {  // what fluid_ui.h:116-150 reads
 		check(euler_readback(sim_, EULER_M, m.data(), m.size()), "readback m");
 		check(euler_readback(sim_, EULER_PRESSURE, pressure.data(), pressure.size()), "readback pressure");

@@ -32,6 +32,28 @@ def test_scene_builder_matches_ui_shell():
         assert_bit_equal(sim.readback(n), getattr(o, n), f"scene {n}")
 
 
+def test_device_set_obstacle_bit_exact(tunnel):
+    """euler_set_obstacle == FluidUI::setObstacle (fluid_ui.h:24-62) on a developed flow: a reset placement, a drag
+    (reset=false -> the disc carries (x - previous x)/dt), a disc poking out of the grid, then a frame of the UI loop."""
+    o = co.make_euler_scene(96, 72, oracle_kind="port")
+    for n in ("u", "v", "m", "solid"):
+        getattr(o, n)[:] = getattr(tunnel, n)
+    sim = gpu_from(o)
+    px, py = 0, 0
+    for (x, y, r, reset) in [(32, 37, 12, True), (36, 34, 12, False), (93, 3, 15, True), (40, 40, 0, True), (38, 41, 10, False)]:
+        vx = np.float32(0 if reset else (x - px) / 1.0)
+        vy = np.float32(0 if reset else (y - py) / 1.0)
+        px, py = x, y
+        o.set_obstacle(x, y, r, vx, vy)
+        sim.setObstacle(x, y, r, reset=reset, dt=1.0)
+        for n in ("solid", "m", "u", "v"):
+            assert_bit_equal(sim.readback(n), getattr(o, n), f"setObstacle({x},{y},{r}) {n}")
+    o.step(40, DT, n_steps=2)
+    sim.step(40, DT, n_steps=2, solver_order=sg.LEX_WAVEFRONT)   # the new solid mask must reach the solver's coefficients
+    for n in ("u", "v", "m", "pressure"):
+        assert_bit_equal(sim.readback(n), getattr(o, n), f"after setObstacle {n}")
+
+
 @pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL, sg.LEX_STRIPS])
 def test_projection_wavefront_bit_identical(tunnel, order):
     o = co.make_euler_scene(96, 72, oracle_kind="port")

@@ -83,3 +83,25 @@ def test_binning_invariants_of_the_oracle():
     for c in np.flatnonzero(cnt > 1)[:500]:
         seg = ids[first[c]:first[c + 1]]
         assert (np.diff(seg) < 0).all()
+
+
+@pytest.mark.parametrize("kind", ["port", "ref"])
+def test_euler_set_obstacle_restatements_agree(kind, has_ref):
+    """FluidUI::setObstacle (fluid_ui.h:24-62) cannot be compiled from the reference (its header needs the windowing
+    engine): the C restatements (port, and the harness acting on the reference's own Fluid object) must equal the
+    independent numpy one, incl. a disc that pokes out of the grid and a dragged obstacle carrying velocity."""
+    if kind == "ref" and not has_ref:
+        pytest.skip("oracle/_ref not built")
+    for (x, y, r, vx, vy) in [(34, 37, 12, 0.0, 0.0), (3, 70, 9, 1.5, -0.25), (95, 2, 20, -3.0, 2.0), (50, 30, 0, 1.0, 1.0)]:
+        a = co.EulerOracle(96, 72, 1000.0, 1 / 100.0, kind=kind)
+        b = co.EulerOracle(96, 72, 1000.0, 1 / 100.0, kind="port")
+        rng = np.random.default_rng(5)
+        for o in (a, b):
+            o.u[:] = rng.standard_normal(o.u.shape).astype(np.float32) if o is a else a.u
+            o.v[:] = 0.5
+            o.m[:] = 0.25
+            o.solid[:] = 1          # stale obstacle everywhere: the call must clear it
+        a.set_obstacle(x, y, r, vx, vy)
+        co.euler_set_obstacle(b, x, y, r, np.float32(vx), np.float32(vy))
+        for n in ("solid", "m", "u", "v"):
+            assert np.array_equal(getattr(a, n), getattr(b, n)), (kind, n, x, y, r)
