@@ -117,6 +117,34 @@ def run_cpu_reference(n_sample, steps, warmup):
 
 
 
+def run_cpu_reference_euler(n_sample=1024, iters=100):
+    """eulerian_fluid's CPU step (oracle/_ref = unmodified fluid.h; else the C port) on a bounded sample of BASELINE
+    configs[1], timed with and without flush-to-zero/denormals-are-zero: SURVEY Q17 -- the reference stalls on denormals
+    while the far field is still quiescent (first steps), so both are reported (8d)."""
+    from oracle import cpu_oracle as co
+    kind = co.best_kind("euler")
+    out = {"kind": "reference" if kind == "ref" else "port", "cores": 1, "unit": "cell-updates/s",
+           "sample": f"wind tunnel at {n_sample}^2 interior cells, {iters} pressure iters, steps 1-2 from the initial state, 1 thread"}
+    for label, ftz in (("ieee", 0), ("ftz_daz", 1)):
+        o = co.make_euler_scene(n_sample, n_sample, oracle_kind=kind)
+        was = o.set_ftz_daz(ftz)
+        secs = []
+        try:
+            for _ in range(2):
+                t0 = time.perf_counter()
+                o.step(iters, 1 / 60.0, 1)
+                secs.append(time.perf_counter() - t0)
+        finally:
+            if was >= 0:
+                o.set_ftz_daz(was)
+        interior = (o.num_x - 2) * (o.num_y - 2)
+        out[label] = {"step1_s": secs[0], "step2_s": secs[1], "step1_cell_updates_per_s": interior * iters / secs[0],
+                      "step2_cell_updates_per_s": interior * iters / secs[1]}
+        o.close()
+    out["value"] = out["ieee"]["step2_cell_updates_per_s"]
+    return out
+
+
 def sharded_solver_bench(rank, world, local_rank, nf=8192, rows_per_rank=1024, iters=200, reps=3):
     """Weak-scaling leg of BASELINE configs[4] (8192^2 with obstacle, 200 SOR sweeps: solver- and halo-bound): the grid is
     cut into `world` slabs of rows_per_rank rows; the velocity halos (9 rows) are exchanged with both neighbours every 8 colour passes over
@@ -596,6 +624,7 @@ def product_arm(args, rank, world, local_rank):
     if world == 1:
         line["eulerian_s1"] = eulerian_bench(local_rank)
     if world == 1 and not args.no_cpu_baseline:
+        line["eulerian_s1"]["cpu_baseline"] = run_cpu_reference_euler()
         n_sample = 1024
         r = run_cpu_reference(n_sample, 3, 0)
         line["cpu_baseline"] = {

@@ -224,6 +224,11 @@ class EulerOracle:
         fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
         fn(self.h_, int(x), int(y), int(r), vx, vy)
 
+    def set_ftz_daz(self, on):
+        """SURVEY Q17 timing aid: flush-to-zero + denormals-are-zero on the calling thread; returns the old setting."""
+        fn = self._fn("set_ftz_daz"); fn.argtypes = [C.c_int]; fn.restype = C.c_int
+        return fn(1 if on else 0)
+
     def step(self, iters, dt, n_steps=1, timed=False):
         """solve -> extrapolate -> advectVel -> advectSmoke (fluid_ui.h:107-111)."""
         fn = self._fn("step"); fn.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_double)]

@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#endif
 
 enum { U_FIELD = 0, V_FIELD = 1, S_FIELD = 2 }; /* fluid.h:33-37 */
 
@@ -184,6 +187,19 @@ void orceuler_set_obstacle(void* h, int x, int y, int r, float vx, float vy) {
 			}
 		}
 	}
+}
+
+/* SURVEY Q17 timing aid (see oracle/ref_harness_euler.cpp): MXCSR FTZ|DAZ of the calling thread; returns the old setting. */
+int orceuler_set_ftz_daz(int on) {
+#if defined(__x86_64__) || defined(__i386__)
+	unsigned csr = _mm_getcsr();
+	int was = (csr & 0x8040u) == 0x8040u;
+	_mm_setcsr(on ? (csr | 0x8040u) : (csr & ~0x8040u));
+	return was;
+#else
+	(void)on;
+	return -1;
+#endif
 }
 
 /* caller sequence, eulerian_fluid/src/fluid_ui.h:107-111 */

@@ -9,6 +9,9 @@
 // leaves them uninitialised, fluid.h:50-68).
 #include <cstring>
 #include <chrono>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#endif
 #include "fluid.h"
 
 extern "C" {
@@ -55,6 +58,20 @@ void refeuler_set_obstacle(void* h, int x, int y, int r, float vx, float vy) {
 				f->solid[c] = true; f->m[c] = 1.f; f->u[c] = vx; f->v[c] = vy;
 			}
 		}
+}
+// on x86 the reference's solve stalls on denormals over large quiescent regions.  Flip the calling
+// thread's MXCSR flush-to-zero (bit 15) + denormals-are-zero (bit 6) so the bench can time the reference both ways;
+// returns the previous setting (0/1), -1 where MXCSR does not exist.  Timing aid only: parity runs never enable it.
+int refeuler_set_ftz_daz(int on) {
+#if defined(__x86_64__) || defined(__i386__)
+	unsigned csr = _mm_getcsr();
+	int was = (csr & 0x8040u) == 0x8040u;
+	_mm_setcsr(on ? (csr | 0x8040u) : (csr & ~0x8040u));
+	return was;
+#else
+	(void)on;
+	return -1;
+#endif
 }
 // caller sequence of eulerian_fluid/src/fluid_ui.h:107-111
 void refeuler_step(void* h, int iters, float dt, int n_steps, double* phase_ns) {

@@ -24,3 +24,20 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_eulerian_cpu_baseline_reports_both_denormal_modes():
+    """the Eulerian CPU baseline is timed with and without FTZ/DAZ; the calling thread's mode is restored."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import cpu_oracle as co
+    probe = co.EulerOracle(4, 4, 1000.0, 0.01)
+    before = probe.set_ftz_daz(0)
+    probe.set_ftz_daz(before)
+    r = bench.run_cpu_reference_euler(n_sample=48, iters=5)
+    assert r["cores"] == 1 and r["kind"] in ("reference", "port") and r["unit"] == "cell-updates/s"
+    for mode in ("ieee", "ftz_daz"):
+        assert r[mode]["step1_s"] > 0 and r[mode]["step2_cell_updates_per_s"] > 0
+    assert r["value"] == r["ieee"]["step2_cell_updates_per_s"]
+    after = probe.set_ftz_daz(before)
+    assert after == before
