@@ -535,6 +535,7 @@ __global__ void __launch_bounds__(kThreads) k_fixup_grid(int n_cells, const int*
 // bit-stable.  The per-particle arithmetic is the reference's; only the order of the adds into a node
 // differs (slot order instead of caller order).  du, dv and particle_density are one array here: the
 // reference computes the same weights three times (bit-equal except aliased border cells).
+template <bool FAST>
 __global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict__ gfirst, const int* __restrict__ gidx,
                                                     const float2* __restrict__ pos, const float2* __restrict__ vel,
                                                     const int* __restrict__ cell_type, float* __restrict__ u,
@@ -546,6 +547,33 @@ __global__ void __launch_bounds__(256) k_p2g_gather(Geo g, const int* __restrict
 	if (i >= g.nx || j >= g.ny1) return;
 	float su = 0.f, sv = 0.f, sw = 0.f;
 	int cx0 = max(i - 1, 0);
+	if (FAST && i >= 1 && i <= g.nx - 3 && j - 1 > g.gy0 && j < g.gy1 - 1 && j <= g.ny - 3) {
+		// Interior node: the four base cells (i-1..i, j-1..j) are all left of / below the aliased last column / row
+		// (Q13), so every particle listed under cell (cx, cy) has x0 == cx, x1 == cx+1, y0 == cy, y1 == cy+1 (the list
+		// key IS (x0, y0), k_collide_mark; the edge rows of a shard's window, which also collect strays, are excluded)
+		// and reaches this node with exactly one weight, known from the cell alone:
+		// no index conversion, no match tests.  Same expressions and the same order of adds as the general loop.
+#pragma unroll
+		for (int r = 0; r < 2; r++) {
+			const int cy = j - 1 + r;
+			const int a = gfirst[(i - 1) + g.nx * cy], mid = gfirst[i + g.nx * cy], b = gfirst[i + g.nx * cy + 1];
+			const float fy = (float)cy;
+			for (int k = a; k < b; k++) {
+				int t = gidx[k];
+				float2 pp = pos[t];
+				float2 pv = vel[t];
+				const bool own = k >= mid;  // listed under cell i (weight sx) or under cell i-1 (weight tx)
+				float x = clampf(pp.x, g.h, g.xmax_c), y = clampf(pp.y, g.h, g.ymax_c);
+				float xs = x - g.h2, ys = y - g.h2;
+				float tx = g.inv_h * (xs - g.h * (float)(own ? i : i - 1));
+				float ty = g.inv_h * (ys - g.h * fy);
+				float wx = own ? 1.f - tx : tx;
+				float wy = r == 1 ? 1.f - ty : ty;
+				float w = wx * wy;
+				su += pv.x * w; sv += pv.y * w; sw += w;
+			}
+		}
+	} else
 	for (int cy = max(j - 1, g.gy0); cy <= j; cy++) {
 		int a = gfirst[cx0 + g.nx * cy], b = gfirst[i + g.nx * cy + 1];
 		for (int k = a; k < b; k++) {
@@ -1261,9 +1289,16 @@ int p2g(FlipSim* f) {
 	if (f->exact_order)
 		k_p2g_gather_exact<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->orig[c], f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
 		                                              f->prev_u, f->prev_v, f->dens, f->p);
-	else
-		k_p2g_gather<<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
-		                                        f->prev_u, f->prev_v, f->dens, f->p);
+	else {
+		// FLIPGPU_P2G_V1=1 runs the general loop at every node (A/B timing; results are identical)
+		const char* v1 = getenv("FLIPGPU_P2G_V1");
+		if (v1 && atoi(v1) != 0)
+			k_p2g_gather<false><<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
+			                                               f->prev_u, f->prev_v, f->dens, f->p);
+		else
+			k_p2g_gather<true><<<grid, block, 0, f->st>>>(g, f->gfirst, f->src, f->pos[c], f->vel[c], f->cell_type, f->u, f->v,
+			                                              f->prev_u, f->prev_v, f->dens, f->p);
+	}
 	f->lc.n++;
 	if (!f->rest_seen && f->sharded) {
 		FG_TRY(shard_rest_latch(f));
