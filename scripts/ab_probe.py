@@ -8,7 +8,7 @@ import simsandgames_b200 as sg
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-SWITCHES = ("FLIPGPU_SEP_V1", "FLIPGPU_G2P_V1")
+SWITCHES = ("FLIPGPU_P2G_V1",)   # every *_V1 switch the library currently reads
 sim, kw, g = sg.scenes.make_flip_tank("synthetic", N=N)
 pos0 = sim.readback("particle_pos").copy()
 zeros_v = np.zeros_like(pos0)

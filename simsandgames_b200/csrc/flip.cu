@@ -334,7 +334,7 @@ __global__ void k_init_colors(int n, float* c) {  // flip_fluid.h:94-96
 // CURRENT position as :208-213, bins from before the first sweep as Q6).  Neighbours are visited
 // row by row in slot order; oracle/flip_oracle.c:orcflip_separate_jacobi is the same schedule on the CPU
 // and this kernel is bit-exact against it.  Statistical distance to the serial sweep: tests T3.
-template <bool COLORS, bool FAST>
+template <bool COLORS>
 __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
                                                        float2* __restrict__ pos_out, const float* __restrict__ col_in,
                                                        float* __restrict__ col_out) {
@@ -361,43 +361,22 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 		// Two passes per chunk of 32 candidates keep the warp converged: pass 1 is the cheap distance test and leaves
 		// a bit mask of overlapping partners; pass 2 runs the sqrt/divide push only for the set bits, in candidate
 		// order (the order of the adds is part of the schedule: oracle orcflip_separate_jacobi).
-		if (FAST && n_all <= 32) {
-			// Common case: the whole window fits one 32-bit mask.  Pass 1 walks each row through its own pointer
-			// (independent loads, no index arithmetic per candidate); a particle never hits itself because its own
-			// d2 is exactly 0.  Pass 2 decodes the candidate number branch-free.  Same candidates, same order of adds.
+		for (int base = 0; base < n_all; base += 32) {
+			const int n = min(32, n_all - base);
 			unsigned hits = 0;
-			int off = 0;
-#pragma unroll
-			for (int r = 0; r < 3; r++) {
-				const float2* __restrict__ q = pos_in + ra[r];
-				const int n = rn[r];
-				unsigned m = 0;
-				// the verdict of candidate i is shifted in from the top and ends up at bit 32 - n + i
-#define FG_SEP_TEST(qq)                                                               \
-	{                                                                                 \
-		float dx = (qq).x - p.x, dy = (qq).y - p.y;                                   \
-		float d2 = dx * dx + dy * dy;                                                 \
-		m = __funnelshift_r(m, !(d2 > min_dist_sq || d2 == 0.f) ? 1u : 0u, 1);        \
-	}
-				int i = 0;
-				for (; i + 4 <= n; i += 4) {  // four independent loads in flight
-					float2 q0 = q[i], q1 = q[i + 1], q2 = q[i + 2], q3 = q[i + 3];
-					FG_SEP_TEST(q0) FG_SEP_TEST(q1) FG_SEP_TEST(q2) FG_SEP_TEST(q3)
-				}
-				for (; i < n; i++) {
-					float2 q0 = q[i];
-					FG_SEP_TEST(q0)
-				}
-#undef FG_SEP_TEST
-				if (rn[r] > 0) hits |= (m >> (32 - rn[r])) << off;  // rn[r] > 0 and n_all <= 32 => off < 32
-				off += rn[r];
+			for (int i = 0; i < n; i++) {
+				int k = base + i;
+				int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
+				float2 q = pos_in[j];
+				float dx = q.x - p.x, dy = q.y - p.y;
+				float d2 = dx * dx + dy * dy;
+				if (j != t && !(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
 			}
-			const int e0 = rn[0], e1 = rn[0] + rn[1];  // candidate numbers where rows 1 and 2 start
-			const int a0 = ra[0], a1 = ra[1] - e0, a2 = ra[2] - e1;
 			while (hits) {
-				int k = __ffs(hits) - 1;
+				int i = __ffs(hits) - 1;
 				hits &= hits - 1;
-				int j = k + (k < e0 ? a0 : (k < e1 ? a1 : a2));
+				int k = base + i;
+				int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
 				float2 q = pos_in[j];
 				float dx = q.x - p.x, dy = q.y - p.y;
 				float d2 = dx * dx + dy * dy;
@@ -410,38 +389,6 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 					c0 += .001f * ((c0 + q0) / 2.f - c0);
 					c1 += .001f * ((c1 + q1) / 2.f - c1);
 					c2 += .001f * ((c2 + q2) / 2.f - c2);
-				}
-			}
-		} else {
-			for (int base = 0; base < n_all; base += 32) {
-				const int n = min(32, n_all - base);
-				unsigned hits = 0;
-				for (int i = 0; i < n; i++) {
-					int k = base + i;
-					int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
-					float2 q = pos_in[j];
-					float dx = q.x - p.x, dy = q.y - p.y;
-					float d2 = dx * dx + dy * dy;
-					if (j != t && !(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
-				}
-				while (hits) {
-					int i = __ffs(hits) - 1;
-					hits &= hits - 1;
-					int k = base + i;
-					int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
-					float2 q = pos_in[j];
-					float dx = q.x - p.x, dy = q.y - p.y;
-					float d2 = dx * dx + dy * dy;
-					float d = sqrtf(d2);
-					float sc = .5f * (min_dist - d) / d;
-					ax -= dx * sc;
-					ay -= dy * sc;
-					if (COLORS) {  // colour diffusion toward the pair mean, flip_fluid.h:239-245
-						float q0 = col_in[3 * (size_t)j], q1 = col_in[3 * (size_t)j + 1], q2 = col_in[3 * (size_t)j + 2];
-						c0 += .001f * ((c0 + q0) / 2.f - c0);
-						c1 += .001f * ((c1 + q1) / 2.f - c1);
-						c2 += .001f * ((c2 + q2) / 2.f - c2);
-					}
 				}
 			}
 		}
@@ -626,50 +573,15 @@ __global__ void k_rest_latch(int n_partials, const float* __restrict__ partials,
 }
 
 // ------------------------------------------------------------------ F8: G2P (flip_fluid.h:404-429)
+// PIC/FLIP blend gather.  Every gather is issued before the first use (one memory round trip after the position
+// instead of three dependent ones: 1.28 -> 0.77 ms at S2), and the -x / -y neighbour types of the validity test
+// :406-409 are taken from the stencil's own nodes where they coincide:
+// cell_type[n1-1] is node 0 and cell_type[n2-1] is node 3 whenever x1 == x0+1, cell_type[n3-nx] is node 0 and
+// cell_type[n2-nx] is node 1 whenever y1 == y0+1 (they differ only in the aliased last column / row, Q13).
 __global__ void __launch_bounds__(kThreads) k_g2p(Geo g, const float2* __restrict__ pos, float2* __restrict__ vel,
                                                   const float* __restrict__ u, const float* __restrict__ v,
                                                   const float* __restrict__ prev_u, const float* __restrict__ prev_v,
                                                   const int* __restrict__ cell_type, float flip_ratio) {
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
-		float2 p = pos[t];
-		float2 pv = vel[t];
-		Stencil st = make_stencil(g, p.x, p.y);
-		int n0 = st.x0 + g.nx * st.y0, n1 = st.x1 + g.nx * st.y0, n2 = st.x1 + g.nx * st.y1, n3 = st.x0 + g.nx * st.y1;
-		int ct0 = cell_type[n0], ct1 = cell_type[n1], ct2 = cell_type[n2], ct3 = cell_type[n3];
-#pragma unroll
-		for (int comp = 0; comp < 2; comp++) {
-			const float* f = comp == 0 ? u : v;
-			const float* pf = comp == 0 ? prev_u : prev_v;
-			int off = comp == 0 ? 1 : g.nx;
-			// Q3: the reference reads cell_type[n-off] below index 0 when y0==0; policy: out of range => not fluid
-			float k0 = (ct0 == FLUID_CELL || (n0 - off >= 0 && cell_type[n0 - off] == FLUID_CELL)) ? 1.f : 0.f;
-			float k1 = (ct1 == FLUID_CELL || (n1 - off >= 0 && cell_type[n1 - off] == FLUID_CELL)) ? 1.f : 0.f;
-			float k2 = (ct2 == FLUID_CELL || (n2 - off >= 0 && cell_type[n2 - off] == FLUID_CELL)) ? 1.f : 0.f;
-			float k3 = (ct3 == FLUID_CELL || (n3 - off >= 0 && cell_type[n3 - off] == FLUID_CELL)) ? 1.f : 0.f;
-			float dsum = k0 * st.w0 + k1 * st.w1 + k2 * st.w2 + k3 * st.w3;
-			if (dsum > 0.f) {
-				float f0 = f[n0], f1 = f[n1], f2 = f[n2], f3 = f[n3];
-				float pic = (k0 * st.w0 * f0 + k1 * st.w1 * f1 + k2 * st.w2 * f2 + k3 * st.w3 * f3) / dsum;
-				float corr = (k0 * st.w0 * (f0 - pf[n0]) + k1 * st.w1 * (f1 - pf[n1]) + k2 * st.w2 * (f2 - pf[n2]) +
-				              k3 * st.w3 * (f3 - pf[n3])) / dsum;
-				float cur = comp == 0 ? pv.x : pv.y;
-				float flipv = cur + corr;
-				float nv = (1.f - flip_ratio) * pic + flip_ratio * flipv;
-				if (comp == 0) pv.x = nv; else pv.y = nv;
-			}
-		}
-		vel[t] = pv;
-	}
-}
-
-// Same arithmetic with every gather issued before the first use (one memory round trip after the position instead
-// of three dependent ones), and the -x / -y neighbour types taken from the stencil's own nodes where they coincide:
-// cell_type[n1-1] is node 0 and cell_type[n2-1] is node 3 whenever x1 == x0+1, cell_type[n3-nx] is node 0 and
-// cell_type[n2-nx] is node 1 whenever y1 == y0+1 (they differ only in the aliased last column / row, Q13).
-__global__ void __launch_bounds__(kThreads) k_g2p_hoisted(Geo g, const float2* __restrict__ pos, float2* __restrict__ vel,
-                                                          const float* __restrict__ u, const float* __restrict__ v,
-                                                          const float* __restrict__ prev_u, const float* __restrict__ prev_v,
-                                                          const int* __restrict__ cell_type, float flip_ratio) {
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
 		float2 p = pos[t];
 		float2 pv = vel[t];
@@ -1228,17 +1140,9 @@ int separate(FlipSim* f, int iters, bool colors) {
 	float2* b = f->pos[1 - c];
 	float* ca = colors ? f->col[c] : nullptr;
 	float* cb = colors ? f->col[1 - c] : nullptr;
-	// FLIPGPU_SEP_V1=1 selects the generic chunked loop for every window (A/B timing; results are identical)
-	const char* sep_v1 = getenv("FLIPGPU_SEP_V1");
-	const bool fast = !(sep_v1 && atoi(sep_v1) != 0);
 	for (int it = 0; it < iters; it++) {
-		if (colors) {
-			if (fast) k_separate<true, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb);
-			else k_separate<true, false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb);
-		} else {
-			if (fast) k_separate<false, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr);
-			else k_separate<false, false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr);
-		}
+		if (colors) k_separate<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb);
+		else k_separate<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr);
 		f->lc.n++;
 		std::swap(a, b);
 		std::swap(ca, cb);
@@ -1345,10 +1249,7 @@ int g2p(FlipSim* f, float flip_ratio) {
 	Geo g = geo(f);
 	if (g.np == 0) return FLIPGPU_OK;
 	int c = f->cur;
-	// FLIPGPU_G2P_V1=1 selects the straightforward kernel (A/B timing; results are identical)
-	const char* v1 = getenv("FLIPGPU_G2P_V1");
-	if (v1 && atoi(v1) != 0) k_g2p<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio);
-	else k_g2p_hoisted<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio);
+	k_g2p<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio);
 	f->lc.n++;
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
