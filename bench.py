@@ -611,8 +611,10 @@ def product_arm(args, rank, world, local_rank):
                 "what": "per step: flip_upload(s) H2D + flip_step + flip_readback_pos_async(particle_pos, caller order) D2H into double-buffered pinned frames; the copy of frame k overlaps the simulation of frame k+1, every frame is waited for"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "sor_gs_tiled_kernel (+ sor_prep_kernel; whole 50-iteration solve in one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches},
+                     "frac": achieved / peak, "traffic": TRAFFIC_NCU if (args.grid == BENCH_N and world == 1) else None,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload "
+                                       "(profiles/r1_final_ncu_flip_4096.md); temporal blocking keeps it ~150x below the algorithmic bytes",
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches},
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / s_per_step / 1e9, "unit": "GB/s",
                           "frac_of_measured": step_bytes / s_per_step / 1e9 / peak, "frac_of_8TBs": step_bytes / s_per_step / 8e12,
                           "formula": "140*P + (96+36*iters)*C  (SURVEY 8d)"},
