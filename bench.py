@@ -307,8 +307,18 @@ def sharded_flip_bench(args, rank, world, local_rank):
     e2e_ms = float(t.item())
     cnt = torch.tensor([n_own], dtype=torch.int64, device="cuda"); dist.all_reduce(cnt)
     assert int(cnt.item()) == P0 * world, "particles lost or duplicated across ranks"
+    phases = None
+    if os.environ.get("FLIPGPU_BENCH_PHASES") == "1":
+        # opt-in diagnostic pass (untimed): rank 0's CUDA-event phases of the sharded step; the exchanges are booked on
+        # the phase they feed (particles -> integrate_bin, post-P2G rows -> p2g, post-solve rows -> g2p)
+        reseed(); barrier()
+        sim.enable_timings(True); sim.reset_timings()
+        sim.simulate(**kw, n_steps=SEG)
+        barrier()
+        phases = {k: v / SEG for k, v in sim.timings().items()}
+        sim.enable_timings(False)
     j0, j1, halo, band, exchanges = sim.shard_info()
-    info = dict(ms_total=ms_max, P_global=P0 * world, P_per_gpu=P0, launches=launches, e2e_ms=e2e_ms, e2e_steps=e2e_steps,
+    info = dict(phase_ms_per_step=phases, ms_total=ms_max, P_global=P0 * world, P_per_gpu=P0, launches=launches, e2e_ms=e2e_ms, e2e_steps=e2e_steps,
                 h2d=int(h_s.numel() * 4), d2h=int(n_own * 8), halo_rows=halo, ghost_band_rows=band, nccl_exchanges=exchanges,
                 grid=[N, N * world], clocks=clk)
     sim.close()
@@ -475,6 +485,8 @@ def product_arm(args, rank, world, local_rank):
                              "formula": "140*P + (96+36*iters)*C per GPU (SURVEY 8d)"},
                 "sharded_solver": shard,
             }
+            if info.get("phase_ms_per_step"):
+                line["phase_ms_per_step"] = info["phase_ms_per_step"]
             print(json.dumps(line), flush=True)
         dist.destroy_process_group()
         return

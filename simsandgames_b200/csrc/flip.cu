@@ -1402,24 +1402,39 @@ int shard_step(FlipSim* f, const FlipStepParams* sp) {
 	FG_CHECK(sp->solver_order == FLIP_SOLVER_RED_BLACK, FLIPGPU_EINVAL, "a sharded simulation runs the red-black order (the lexicographic wavefront does not shard)");
 	FG_CHECK(!sp->update_colors, FLIPGPU_EINVAL, "render-state colours are not kept in sharded mode");
 	const float cp = f->d.density * f->d.h / sp->dt;
+	// phase timings (flip_enable_timings): the exchanges are booked on the phase they feed -- particle exchange under
+	// integrate_bin, post-P2G halo rows under p2g, post-solve halo rows under g2p
+	if (f->timings_on) collect_slot(f, f->ev_slot);
+	phase_mark(f, FLIP_PH_INTEGRATE_BIN);
 	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity));              // migrants change owner, ghosts are refreshed
 	// (the exchange synchronised the stream, so the previous step -- and its copy of the rest density -- is complete on
 	// every rank: all ranks take the same branch below and issue the same NCCL calls)
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
 	FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));         // owned + ghosts
+	phase_mark(f, FLIP_PH_SEPARATE);
 	if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, false));
+	phase_mark(f, FLIP_PH_COLLIDE_MARK);
 	FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
+	phase_mark(f, FLIP_PH_P2G);
 	FG_TRY(p2g(f));                                                        // own node rows
 	{	// the rows next to the slab come from their owners: post-P2G fields, cell types, densities, s
 		void* fields[] = {f->u, f->v, f->prev_u, f->prev_v, f->dens, f->cell_type, f->s};
 		FG_TRY(shard_exchange_rows(f, fields, 7, f->halo));
 	}
+	phase_mark(f, FLIP_PH_SOLVE);
 	FG_TRY(shard_solve(f, sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0));
+	phase_mark(f, FLIP_PH_G2P);
 	{	// post-solve velocities (and the pressure) of the halo rows, for the G2P of particles near the boundary
 		void* fields[] = {f->u, f->v, f->p};
 		FG_TRY(shard_exchange_rows(f, fields, 3, f->halo));
 	}
 	FG_TRY(g2p(f, sp->flip_ratio));
+	phase_mark(f, FLIP_PH_COLORS);
+	phase_mark(f, FLIP_PH_COUNT);
+	if (f->timings_on) {
+		f->ev_pending[f->ev_slot] = true;
+		f->ev_slot = (f->ev_slot + 1) % FlipSim::kEvRing;
+	}
 	return FLIPGPU_OK;
 }
 
