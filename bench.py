@@ -587,6 +587,24 @@ def product_arm(args, rank, world, local_rank):
     h_pos = h_frames[(e2e_steps - 1) % 2]
     assert bool(torch.isfinite(h_pos[:1024]).all())
 
+    # context for the e2e figure: what a bare pinned device->host copy of one frame achieves on this box (diagnostic only)
+    d2h_link = None
+    try:
+        d_probe = torch.empty(2 * P, dtype=torch.float32, device=torch.device("cuda", local_rank))
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            h_frames[0].copy_(d_probe, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            best = max(best, d_probe.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+        d2h_link = best
+        del d_probe
+    except Exception:   # never let a diagnostic break the bench line
+        d2h_link = None
+
     sim.close()
     shard = sharded_solver_bench(rank, world, local_rank) if (world > 1 or args.with_shard_bench) else None
     if rank != 0:
@@ -619,7 +637,7 @@ def product_arm(args, rank, world, local_rank):
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                    "samples": clk["samples"], "power_w_max": clk.get("power_w_max")},
         "e2e": {"value": world * P * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_s.numel() * 4),
-                "d2h_bytes_per_step": int(h_pos.numel() * 4), "steps": e2e_steps,
+                "d2h_bytes_per_step": int(h_pos.numel() * 4), "steps": e2e_steps, "d2h_link_GBps_bare_copy": d2h_link,
                 "what": "per step: flip_upload(s) H2D + flip_step + flip_readback_pos_async(particle_pos, caller order) D2H into double-buffered pinned frames; the copy of frame k overlaps the simulation of frame k+1, every frame is waited for"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "sor_gs_tiled_kernel (+ sor_prep_kernel; whole 50-iteration solve in one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
