@@ -85,6 +85,7 @@ int sor_rb_prep(SorWorkspace** ws, const SorGrid& g, bool drift, int row_lo, int
 int sor_rb_round(SorWorkspace* w, const SorGrid& g, float* out_f, float* out_s, float* out_p, int passes, int colour0, int row_lo,
                  int row_hi, float cp, float omega, bool drift, cudaStream_t st, LaunchCounter* lc);
 int sor_rb_passes_per_round();
+int sor_rb_deactivate_rows(SorWorkspace* w, const SorGrid& g, int row_lo, int row_hi, cudaStream_t st);
 void sor_rb_rows_launch(const SorGrid& g, int colour, int shift, int lo, int hi, float cp, float omega, bool drift, cudaStream_t st);
 int sor_residual(const SorGrid& g, bool drift, float* d_partials, int n_partials, float* h_out2, cudaStream_t st,
                  LaunchCounter* lc);

@@ -67,6 +67,9 @@ struct SorShard {
 	int halo = 9;  // H halo rows per side -> K = H-1 colour passes between exchanges
 	bool x_fast = true;
 	float *vel_f = nullptr, *vel_s = nullptr, *p = nullptr, *s = nullptr, *dens = nullptr, *d_rest = nullptr;
+	float *alt_f = nullptr, *alt_s = nullptr, *alt_p = nullptr;  // ping-pong partners (tiled red-black rounds, lazy)
+	SorWorkspace* ws = nullptr;
+	bool s_binary = true;  // every uploaded s value was 0 or 1 (the tiled kernel's 1-byte cell code needs that)
 	int* cell_type = nullptr;
 	ncclComm_t comm = nullptr;
 	cudaStream_t st = nullptr;
@@ -158,8 +161,9 @@ int sorshard_destroy(SorShard* h) {
 	SDeviceGuard guard(h->device);
 	cudaStreamSynchronize(h->st);
 	if (h->comm) g_nccl.CommDestroy(h->comm);
-	void* ptrs[] = {h->vel_f, h->vel_s, h->p, h->s, h->dens, h->cell_type, h->d_rest};
+	void* ptrs[] = {h->vel_f, h->vel_s, h->p, h->s, h->dens, h->cell_type, h->d_rest, h->alt_f, h->alt_s, h->alt_p};
 	for (void* p : ptrs) if (p) cudaFree(p);
+	sor_workspace_free(h->ws);
 	cudaStreamDestroy(h->st);
 	delete h;
 	return FLIPGPU_OK;
@@ -182,6 +186,10 @@ static int shard_copy(SorShard* h, int field, void* host, int j_start, int n_row
 	SDeviceGuard guard(h->device);
 	size_t off = (size_t)(j_start - (h->j0 - h->halo)) * h->nf * elem, bytes = (size_t)n_rows * h->nf * elem;
 	if (bytes) {
+		if (to_device && field == SORSHARD_S) {
+			const float* sv = (const float*)host;
+			for (size_t i = 0, n = (size_t)n_rows * h->nf; i < n && h->s_binary; i++) h->s_binary = sv[i] == 0.f || sv[i] == 1.f;
+		}
 		if (to_device) FG_CUDA(cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, h->st));
 		else FG_CUDA(cudaMemcpyAsync(host, base + off, bytes, cudaMemcpyDeviceToHost, h->st));
 	}
@@ -211,27 +219,57 @@ int sorshard_solve(SorShard* h, int iters, float cp, float omega, int drift, flo
 	dim3 block(64, 4);
 	const unsigned gx = cdiv((size_t)(h->nf + 1) / 2 + 1, block.x);
 	const size_t blk = (size_t)H * h->nf;  // one exchange block: H rows
+	// refresh the halos: my H outermost own rows go to the neighbour's halo, its rows come into mine
+	auto exchange = [&]() -> int {
+		float* fields[2] = {h->vel_f, h->vel_s};
+		FG_NCCL(g_nccl.GroupStart());
+		for (float* f : fields) {
+			if (has_up) {
+				FG_NCCL(g_nccl.Send(f + (size_t)(h->rows - 2 * H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
+				FG_NCCL(g_nccl.Recv(f + (size_t)(h->rows - H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
+			}
+			if (has_down) {
+				FG_NCCL(g_nccl.Send(f + (size_t)H * h->nf, blk, ncclFloat, h->rank - 1, h->comm, h->st));
+				FG_NCCL(g_nccl.Recv(f, blk, ncclFloat, h->rank - 1, h->comm, h->st));
+			}
+		}
+		FG_NCCL(g_nccl.GroupEnd());
+		h->exchanges++;
+		return FLIPGPU_OK;
+	};
+	// OPT-IN (FLIPGPU_SHARD_TILED=1, not yet validated on hardware): one launch of the temporally blocked red-black
+	// kernel per exchange -- its 8 colour passes are exactly what the 9-row halo allows -- as the sharded FLIP step
+	// already does (flip.cu shard_solve).  Rows of the local window that are the global border, or outside the grid,
+	// are deactivated; output = own rows +- 1 (completes the face rows two slabs share).
+	const char* tiled_env = getenv("FLIPGPU_SHARD_TILED");
+	if (tiled_env && atoi(tiled_env) != 0 && h->nranks > 1 && h->s_binary && K == sor_rb_passes_per_round()) {
+		const size_t n = (size_t)h->nf * h->rows;
+		if (!h->alt_f) {
+			float** alts[] = {&h->alt_f, &h->alt_s, &h->alt_p};
+			for (float** a : alts) {
+				FG_CUDA(cudaMalloc(a, n * 4));
+				FG_CUDA(cudaMemsetAsync(*a, 0, n * 4, h->st));
+			}
+		}
+		FG_TRY(sor_rb_prep(&h->ws, g, use_drift, 0, h->rows, h->st, &h->lc));
+		FG_TRY(sor_rb_deactivate_rows(h->ws, g, 0, 1 - base, h->st));                // global rows <= 0
+		FG_TRY(sor_rb_deactivate_rows(h->ws, g, h->ns - 1 - base, h->rows, h->st));  // global rows >= ns-1
+		const int out_lo = (has_down ? h->j0 - 1 : h->j0) - base, out_hi = (has_up ? h->j1 + 1 : h->j1) - base;
+		for (int pass0 = 0; pass0 < 2 * iters; pass0 += K) {
+			FG_TRY(exchange());
+			g.vel_f = h->vel_f; g.vel_s = h->vel_s; g.p = h->p;
+			FG_TRY(sor_rb_round(h->ws, g, h->alt_f, h->alt_s, h->alt_p, std::min(K, 2 * iters - pass0), (pass0 & 1) ^ shift, out_lo, out_hi,
+			                    cp, omega, use_drift, h->st, &h->lc));
+			std::swap(h->vel_f, h->alt_f); std::swap(h->vel_s, h->alt_s); std::swap(h->p, h->alt_p);
+		}
+		FG_CUDA(cudaGetLastError());
+		return FLIPGPU_OK;
+	}
 	int pass = 0;
 	for (int it = 0; it < iters; it++)
 		for (int colour = 0; colour < 2; colour++, pass++) {
 			const int m = h->nranks > 1 ? pass % K : 0;
-			if (h->nranks > 1 && m == 0) {
-				// refresh the halos: my H outermost own rows go to the neighbour's halo, its rows come into mine
-				float* fields[2] = {h->vel_f, h->vel_s};
-				FG_NCCL(g_nccl.GroupStart());
-				for (float* f : fields) {
-					if (has_up) {
-						FG_NCCL(g_nccl.Send(f + (size_t)(h->rows - 2 * H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
-						FG_NCCL(g_nccl.Recv(f + (size_t)(h->rows - H) * h->nf, blk, ncclFloat, h->rank + 1, h->comm, h->st));
-					}
-					if (has_down) {
-						FG_NCCL(g_nccl.Send(f + (size_t)H * h->nf, blk, ncclFloat, h->rank - 1, h->comm, h->st));
-						FG_NCCL(g_nccl.Recv(f, blk, ncclFloat, h->rank - 1, h->comm, h->st));
-					}
-				}
-				FG_NCCL(g_nccl.GroupEnd());
-				h->exchanges++;
-			}
+			if (h->nranks > 1 && m == 0) FG_TRY(exchange());
 			// rows whose inputs are still exact: own rows plus a halo band that shrinks by one row per pass
 			int lo = has_down ? h->j0 - (H - 1) + m : h->j0, hi = has_up ? h->j1 + (H - 1) - m - 1 : h->j1 - 1;
 			lo = std::max(lo, 1); hi = std::min(hi, h->ns - 2);

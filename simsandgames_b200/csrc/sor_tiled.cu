@@ -508,6 +508,14 @@ int sor_rb_round(SorWorkspace* w, const SorGrid& g, float* out_f, float* out_s, 
 	return FLIPGPU_OK;
 }
 int sor_rb_passes_per_round() { return kRbK; }
+// A view whose rows are a WINDOW of a larger grid (the slab of sor_shard.cu) must not update the rows that are the
+// larger grid's border or lie outside it: clear their cell codes after sor_rb_prep.  Rows [row_lo, row_hi) of the view.
+int sor_rb_deactivate_rows(SorWorkspace* w, const SorGrid& g, int row_lo, int row_hi, cudaStream_t st) {
+	row_lo = std::max(row_lo, 0); row_hi = std::min(row_hi, g.ns);
+	if (!w || !w->code || row_hi <= row_lo) return FLIPGPU_OK;
+	FG_CUDA(cudaMemsetAsync(w->code + (size_t)g.nf * row_lo, 0, (size_t)g.nf * (row_hi - row_lo), st));
+	return FLIPGPU_OK;
+}
 
 // ===================================================================================================
 // Streaming-strip variant of the blocked wavefront (same order, same bits; the default).
