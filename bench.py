@@ -558,6 +558,34 @@ def product_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
 
+    # ---- for information: the same step with the red-black order (north_star's named order; temporally blocked kernel).
+    #      Not the headline: at the reference's 50 sweeps red-black leaves the regime the reference stays in earlier than
+    #      the reference's own order (profiles/r1_stability.md), hence the shorter segment.  Guarded: never breaks the line.
+    rb_variant = None
+    try:
+        if world == 1:
+            rb_steps = 8
+            reseed_rb = dict(kw)
+            sim.num_particles = P
+            sim.upload_from("particle_pos", h_pos0.data_ptr(), 2 * P)
+            sim.upload_from("particle_vel", h_zero_p.data_ptr(), 2 * P)
+            for name in ("u", "v", "prev_u", "prev_v", "p", "particle_density"):
+                sim.upload_from(name, h_zero_c.data_ptr(), nx * ny)
+            sim.upload_from("s", h_s.data_ptr(), nx * ny)
+            sim.particle_rest_density = 0.0
+            sim.simulate(**reseed_rb, n_steps=args.warmup, update_colors=False, solver_order=sg.RED_BLACK)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            sim.simulate(**reseed_rb, n_steps=rb_steps, update_colors=False, solver_order=sg.RED_BLACK)
+            r1.record(stream)
+            barrier()
+            rb_ms = r0.elapsed_time(r1) / rb_steps
+            rb_variant = {"solver_order": "red_black (temporally blocked, 8 colour passes per launch)", "ms_per_step": rb_ms,
+                          "value": P / (rb_ms * 1e-3), "unit": UNIT, "steps": rb_steps}
+    except Exception as exc:   # diagnostic only
+        rb_variant = {"error": str(exc)[:200]}
+
     # ---- end to end through the C ABI with HOST buffers (pinned): per step, the caller's per-frame writes go H2D
     #      (the s field that FluidUI::setObstacle rewrites every frame, main.cpp:106-122) and the array the caller
     #      reads every frame comes back D2H (particle_pos, main.cpp:173-176), in caller particle order.
@@ -651,6 +679,8 @@ def product_arm(args, rank, world, local_rank):
         "cell_updates_per_s": world * interior * iters / (solve_ms_per_step * 1e-3),
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
+    if rb_variant is not None:
+        line["red_black_variant"] = rb_variant
     if shard is not None:
         line["sharded_solver"] = shard
     if world == 1:
