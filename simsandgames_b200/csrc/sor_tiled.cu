@@ -53,7 +53,15 @@ __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
 	for (long long spins = 0; *((volatile const int*)flag) != epoch && spins < (1ll << 25); spins++) __nanosleep(64);
 }
 
-template <bool XFAST, bool DRIFT, int KW>  // KW warps per CTA (>= iterations per chunk)
+// ceil(2^16 / d): floor(n / d) == (n * magic[d]) >> 16 for every n < 1024, d <= 32 (checked exhaustively)
+__constant__ unsigned c_div_magic[33] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554,
+                                         5958,  5462,  5042,  4682,  4370,  4096,  3856,  3641, 3450, 3277, 3121,
+                                         2979,  2850,  2731,  2622,  2521,  2428,  2341,  2260, 2185, 2115, 2048};
+
+// V2 (opt-in, FLIPGPU_SOR_V2=1; same work items, same arithmetic, same results): the per-step item decode is two integer
+// instructions instead of an fp32 reciprocal + conversions, and every operand of the cell is fetched in ONE shared-memory
+// round trip (the baseline SASS tests the cell code first and only then loads the operands).
+template <bool XFAST, bool DRIFT, int KW, bool V2>  // KW warps per CTA (>= iterations per chunk)
 __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_kernel(TiledArgs A) {
 	// dynamic shared memory (> 48 KB with the drift term): four float planes and the cell code as a 32-bit word per cell
 	// (a byte plane would put several lanes of a diagonal into one bank)
@@ -137,15 +145,23 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		for (int t = 0; t < 2 * kTile - 1; t++) {
 			const int alo = max(0, t - (kTile - 1)), cnt = min(kTile - 1, t) - alo + 1;
 			if (tid < cnt * kq) {
-				const int k = (int)(((float)tid + 0.5f) * (1.f / (float)cnt));  // tid / cnt: the quotient is >= 1/64 away from an integer
+				const int k = V2 ? (int)(((unsigned)tid * c_div_magic[cnt]) >> 16)
+				                 : (int)(((float)tid + 0.5f) * (1.f / (float)cnt));  // tid / cnt: the quotient is >= 1/64 away from an integer
 				const int a = alo + (tid - k * cnt);
 				{
 					// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
 					int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
 					// every operand is fetched before the activity test: one shared-memory round trip per step instead of two
 					unsigned cd = s_code[e];
-					float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[e + kBoxW], pp = s_p[e];
-					float dr = DRIFT ? s_dr[e] : 0.f;
+					float vfc, vfp, vsc, vsp, pp, dr = 0.f;
+					if (V2) {  // volatile reads cannot be sunk below the activity test: the seven loads go out back to back
+						vfc = *(volatile float*)(s_vf + e); vfp = *(volatile float*)(s_vf + e + 1); vsc = *(volatile float*)(s_vs + e);
+						vsp = *(volatile float*)(s_vs + e + kBoxW); pp = *(volatile float*)(s_p + e);
+						if (DRIFT) dr = *(volatile float*)(s_dr + e);
+					} else {
+						vfc = s_vf[e]; vfp = s_vf[e + 1]; vsc = s_vs[e]; vsp = s_vs[e + kBoxW]; pp = s_p[e];
+						if (DRIFT) dr = s_dr[e];
+					}
 					if (cd & 1u) {
 						float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
 						if (DRIFT) div -= dr;        // the stored term is max(0, density-rest): subtracting 0 is exact
@@ -347,12 +363,13 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	dim3 block(kTile, kw);
 	int per_sm = 0;
 	const void* fn;
-	if (kw == 8)
-		fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, 8> : (const void*)sor_gs_tiled_kernel<true, false, 8>)
-		              : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, 8> : (const void*)sor_gs_tiled_kernel<false, false, 8>);
-	else
-		fn = g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, 16> : (const void*)sor_gs_tiled_kernel<true, false, 16>)
-		              : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, 16> : (const void*)sor_gs_tiled_kernel<false, false, 16>);
+	static const bool v2 = getenv("FLIPGPU_SOR_V2") && atoi(getenv("FLIPGPU_SOR_V2")) != 0;  // opt-in until validated on hardware
+#define FG_TILED_FN(KWV, V2V)                                                                                                          \
+	(g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, KWV, V2V> : (const void*)sor_gs_tiled_kernel<true, false, KWV, V2V>) \
+	          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, KWV, V2V> : (const void*)sor_gs_tiled_kernel<false, false, KWV, V2V>))
+	if (kw == 8) fn = v2 ? FG_TILED_FN(8, true) : FG_TILED_FN(8, false);
+	else fn = v2 ? FG_TILED_FN(16, true) : FG_TILED_FN(16, false);
+#undef FG_TILED_FN
 	const size_t tile_smem = (size_t)kBoxW * kBoxW * 4 * (use_drift ? 5 : 4);
 	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
 	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * kw, tile_smem));
