@@ -85,9 +85,22 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		const int I = tl.x, J = tl.y, q = tl.z, kq = tl.w;
 		long long c0 = clock64();
 		if (tid == 0) {
-			if (I > 0) wait_flag(A.flags + (q * A.nj + J) * A.ni + I - 1, A.epoch);
-			if (J > 0) wait_flag(A.flags + (q * A.nj + J - 1) * A.ni + I, A.epoch);
-			if (q > 0) wait_flag(A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1), A.epoch);
+			if (V2) {
+				// the three predecessor flags are polled together (one L2 round trip per poll instead of up to three in a row),
+				// without sleeping: one thread per CTA spins, and the tile usually sits on the critical path of the wavefront
+				const int* f1 = I > 0 ? A.flags + (q * A.nj + J) * A.ni + I - 1 : nullptr;
+				const int* f2 = J > 0 ? A.flags + (q * A.nj + J - 1) * A.ni + I : nullptr;
+				const int* f3 = q > 0 ? A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1) : nullptr;
+				for (long long spins = 0; spins < (1ll << 27); spins++) {
+					int v1 = f1 ? *((volatile const int*)f1) : A.epoch, v2 = f2 ? *((volatile const int*)f2) : A.epoch,
+					    v3 = f3 ? *((volatile const int*)f3) : A.epoch;
+					if (v1 == A.epoch && v2 == A.epoch && v3 == A.epoch) break;
+				}
+			} else {
+				if (I > 0) wait_flag(A.flags + (q * A.nj + J) * A.ni + I - 1, A.epoch);
+				if (J > 0) wait_flag(A.flags + (q * A.nj + J - 1) * A.ni + I, A.epoch);
+				if (q > 0) wait_flag(A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1), A.epoch);
+			}
 			__threadfence();
 		}
 		__syncthreads();
