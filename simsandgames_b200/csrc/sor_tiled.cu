@@ -421,7 +421,10 @@ struct RbArgs {
 	float cp, omega;
 };
 
-template <bool XFAST, bool DRIFT>
+// V2 (opt-in, FLIPGPU_RB_V2=1; same cells, same arithmetic, same results): a thread's (up to five) cells of one colour pass
+// never share a face, so their codes are fetched together, then the operands of the active ones together, and only then the
+// updates run -- two shared-memory round trips per half pass instead of two per cell.
+template <bool XFAST, bool DRIFT, bool V2>
 __global__ void __launch_bounds__(512, 2) sor_rb_tiled_kernel(RbArgs A) {
 	extern __shared__ float smem_rb[];
 	float* s_f = smem_rb;
@@ -470,6 +473,44 @@ __global__ void __launch_bounds__(512, 2) sor_rb_tiled_kernel(RbArgs A) {
 			const int lx = lxa + 64 * half;
 			if (lx > hi) break;
 			int e = rb_index(lx, ly0), ex = rb_index(lx + 1, ly0);
+			if (V2) {
+				constexpr int R = (kRbW - 2) / 16 + 1;  // rows ly0, ly0+16, ... <= hi <= kRbW-2: at most 5
+				unsigned cd[R];
+				float vfc[R], vfp[R], vsc[R], vsp[R], pp[R], dr[R];
+#pragma unroll
+				for (int r = 0; r < R; r++) cd[r] = (ly0 + 16 * r <= hi) ? (unsigned)s_c[e + r * 16 * kRbRow] : 0u;
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					const int er = e + r * 16 * kRbRow, exr = ex + r * 16 * kRbRow;
+					vfc[r] = vfp[r] = vsc[r] = vsp[r] = pp[r] = dr[r] = 0.f;
+					if (cd[r] & 1u) {
+						vfc[r] = s_f[er]; vfp[r] = s_f[exr]; vsc[r] = s_s[er]; vsp[r] = s_s[er + kRbRow]; pp[r] = s_p[er];
+						if (DRIFT) dr[r] = s_d[er];
+					}
+				}
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					if (!(cd[r] & 1u)) continue;
+					const int er = e + r * 16 * kRbRow, exr = ex + r * 16 * kRbRow, eyr = er + kRbRow;
+					float div = XFAST ? ((vfp[r] - vfc[r]) + vsp[r]) - vsc[r] : ((vsp[r] - vsc[r]) + vfp[r]) - vfc[r];
+					if (DRIFT) div -= dr[r];
+					if (cd[r] == 31u) {
+						float pv = (-div * 0.25f) * A.omega;
+						s_p[er] = pp[r] + A.cp * pv;
+						s_f[er] = vfc[r] - pv; s_f[exr] = vfp[r] + pv; s_s[er] = vsc[r] - pv; s_s[eyr] = vsp[r] + pv;
+					} else {
+						const unsigned c = cd[r];
+						float sfm = (c & 2u) ? 1.f : 0.f, sfp = (c & 4u) ? 1.f : 0.f;
+						float ssm = (c & 8u) ? 1.f : 0.f, ssp = (c & 16u) ? 1.f : 0.f;
+						float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+						float pv = -div / ssum;
+						pv *= A.omega;
+						s_p[er] = pp[r] + A.cp * pv;
+						s_f[er] = vfc[r] - sfm * pv; s_f[exr] = vfp[r] + sfp * pv;
+						s_s[er] = vsc[r] - ssm * pv; s_s[eyr] = vsp[r] + ssp * pv;
+					}
+				}
+			} else
 			for (int ly = ly0; ly <= hi; ly += 16, e += 16 * kRbRow, ex += 16 * kRbRow) {
 				const int ey = e + kRbRow;
 				const unsigned cd = s_c[e];
@@ -528,8 +569,12 @@ int sor_rb_round(SorWorkspace* w, const SorGrid& g, float* out_f, float* out_s, 
 	A.code = w->code; A.drift = use_drift ? w->drift : nullptr; A.row_lo = row_lo; A.row_hi = row_hi;
 	A.passes = std::min(passes, kRbK); A.colour0 = colour0 & 1; A.tiles_x = (g.nf + kRbT - 1) / kRbT; A.cp = cp; A.omega = omega;
 	const int tiles_y = (row_hi - row_lo + kRbT - 1) / kRbT;
-	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_rb_tiled_kernel<true, true> : (const void*)sor_rb_tiled_kernel<true, false>)
-	                          : (use_drift ? (const void*)sor_rb_tiled_kernel<false, true> : (const void*)sor_rb_tiled_kernel<false, false>);
+	static const bool v2 = getenv("FLIPGPU_RB_V2") && atoi(getenv("FLIPGPU_RB_V2")) != 0;  // opt-in until validated on hardware
+#define FG_RB_FN(V2V)                                                                                                                \
+	(g.x_fast ? (use_drift ? (const void*)sor_rb_tiled_kernel<true, true, V2V> : (const void*)sor_rb_tiled_kernel<true, false, V2V>) \
+	          : (use_drift ? (const void*)sor_rb_tiled_kernel<false, true, V2V> : (const void*)sor_rb_tiled_kernel<false, false, V2V>))
+	const void* fn = v2 ? FG_RB_FN(true) : FG_RB_FN(false);
+#undef FG_RB_FN
 	const size_t smem = (size_t)kRbBox * ((use_drift ? 4 : 3) * sizeof(float) + 1);
 	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	void* args[] = {&A};
