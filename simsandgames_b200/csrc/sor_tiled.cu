@@ -84,6 +84,36 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		const int4 tl = A.tiles[ti];
 		const int I = tl.x, J = tl.y, q = tl.z, kq = tl.w;
 		long long c0 = clock64();
+		// V2: the activity of the tile's squares does not depend on the predecessors -- fetch it while waiting for them
+		bool any_pre = false;
+		if (V2)
+			for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
+				for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any_pre |= A.act[jj * A.na + ii] != 0;
+		if (V2 && any_pre) {  // ... and so are the per-solve cell constants: stage the code / drift planes of the box now
+			const int FBp = 1 + I * kTile - A.kc + 1, SBp = 1 + J * kTile - A.kc + 1;
+			constexpr int kRoundsP = (kBoxW * kBoxW + kTile * KW - 1) / (kTile * KW);
+			unsigned p_cd[kRoundsP];
+			float p_dr[kRoundsP];
+#pragma unroll
+			for (int r = 0; r < kRoundsP; r++) {
+				int e = tid + r * nthreads;
+				int F = FBp + e % kBoxW, S = SBp + e / kBoxW;
+				p_cd[r] = 0; p_dr[r] = 0.f;
+				if (e < kBoxW * kBoxW && F >= 0 && F < nf && S >= 0 && S < ns) {
+					size_t c = (size_t)F + (size_t)nf * S;
+					p_cd[r] = A.code[c];
+					if (DRIFT) p_dr[r] = A.drift[c];
+				}
+			}
+#pragma unroll
+			for (int r = 0; r < kRoundsP; r++) {
+				int e = tid + r * nthreads;
+				if (e < kBoxW * kBoxW) {
+					s_code[e] = p_cd[r];
+					if (DRIFT) s_dr[e] = p_dr[r];
+				}
+			}
+		}
 		if (tid == 0) {
 			if (V2) {
 				// the three predecessor flags are polled together (one L2 round trip per poll instead of up to three in a row),
@@ -107,9 +137,10 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		long long c1 = clock64();
 		{	// the skewed tile lies inside the four unskewed squares (I-1..I, J-1..J): if none of them holds an active
 			// cell (all air / solid) the tile changes nothing -- publish it at once (dam-break: about half the tiles)
-			bool any = false;
-			for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
-				for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any |= A.act[jj * A.na + ii] != 0;
+			bool any = any_pre;
+			if (!V2)
+				for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
+					for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any |= A.act[jj * A.na + ii] != 0;
 			if (!any) {
 				if (tid == 0) *((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
 				continue;
@@ -133,16 +164,21 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 				if (e < kBoxW * kBoxW && F >= 0 && F < nf && S >= 0 && S < ns) {
 					size_t c = (size_t)F + (size_t)nf * S;
 					r_vf[r] = __ldcg(A.vel_f + c); r_vs[r] = __ldcg(A.vel_s + c); r_p[r] = __ldcg(A.p + c);
-					r_cd[r] = A.code[c];
-					if (DRIFT) r_dr[r] = A.drift[c];
+					if (!V2) {
+						r_cd[r] = A.code[c];
+						if (DRIFT) r_dr[r] = A.drift[c];
+					}
 				}
 			}
 #pragma unroll
 			for (int r = 0; r < kRounds; r++) {
 				int e = tid + r * nthreads;
 				if (e < kBoxW * kBoxW) {
-					s_vf[e] = r_vf[r]; s_vs[e] = r_vs[r]; s_p[e] = r_p[r]; s_code[e] = r_cd[r];
-					if (DRIFT) s_dr[e] = r_dr[r];
+					s_vf[e] = r_vf[r]; s_vs[e] = r_vs[r]; s_p[e] = r_p[r];
+					if (!V2) {
+						s_code[e] = r_cd[r];
+						if (DRIFT) s_dr[e] = r_dr[r];
+					}
 				}
 			}
 		}
