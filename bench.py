@@ -429,7 +429,11 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "timing": "host steady clock around the reference's simulate()"},
+        "config": {"workload": f"flip_fluid synthetic dam-break {n_sample}^2 grid, {r['particles']} particles, 50 SOR iters, 2 separation sweeps: a bounded CPU "
+                               f"sample of BASELINE configs[2] (same scene rule; the full 4096^2 / 64264080-particle step takes the serial reference "
+                               f"over a minute per step -- bench.py's product arm times one such step as cpu_baseline.full_size)",
+                   "same_config_as_product_arm": False, "grid": [n_sample, n_sample], "particles": r["particles"],
+                   "timing": "host steady clock around the reference's simulate()"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": 1, "kind": r["kind"], "sample": sample,
                          "cell_updates_per_s": r["cell_updates_per_s"], "phase_share": r["phase_share"],
                          "host_cpus": os.cpu_count()},
@@ -598,7 +602,7 @@ def product_arm(args, rank, world, local_rank):
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(stream)
     for k in range(e2e_steps):
-        sim.upload_from("s", h_s.data_ptr(), h_s.numel())                 # H2D: the caller's per-frame grid write
+        sim.upload_from_async("s", h_s.data_ptr(), h_s.numel())           # H2D: the caller's per-frame grid write (queued; h_s is never modified)
         sim.simulate(**kw, n_steps=1, update_colors=False)
         sim.readback_wait()                                                # frame k-1 has landed (its buffer is free again at k+1)
         sim.readback_pos_async(h_frames[k % 2].data_ptr(), 2 * P)          # D2H of frame k overlaps the simulation of frame k+1
@@ -666,7 +670,7 @@ def product_arm(args, rank, world, local_rank):
                    "samples": clk["samples"], "power_w_max": clk.get("power_w_max")},
         "e2e": {"value": world * P * e2e_steps / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h_s.numel() * 4),
                 "d2h_bytes_per_step": int(h_pos.numel() * 4), "steps": e2e_steps, "d2h_link_GBps_bare_copy": d2h_link,
-                "what": "per step: flip_upload(s) H2D + flip_step + flip_readback_pos_async(particle_pos, caller order) D2H into double-buffered pinned frames; the copy of frame k overlaps the simulation of frame k+1, every frame is waited for"},
+                "what": "per step: flip_upload_async(s) H2D + flip_step + flip_readback_pos_async(particle_pos, caller order) D2H into double-buffered pinned frames; positions are un-permuted on a second stream as soon as the collision pass has made them final, so the PCIe copy of frame k overlaps the solve of step k and the start of step k+1; every frame is waited for"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "sor_gs_tiled_kernel (+ sor_prep_kernel; whole 50-iteration solve in one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC_NCU if (args.grid == BENCH_N and world == 1) else None,

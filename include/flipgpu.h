@@ -71,9 +71,12 @@ typedef enum {
 } FlipField;
 
 typedef enum {
-	FLIP_SOLVER_RED_BLACK = 0,     /* performance order (north_star); bounded against the reference order */
-	FLIP_SOLVER_LEX_WAVEFRONT = 1, /* the reference's lexicographic loop order (flip_fluid.h:458-494) as a blocked
-	                                  anti-diagonal wavefront in shared memory: bit-identical u,v,p */
+	FLIP_SOLVER_LEX_WAVEFRONT = 0, /* the reference's lexicographic loop order (flip_fluid.h:458-494) as a blocked
+	                                  anti-diagonal wavefront: bit-identical u,v,p.  Value 0: a zero-initialised
+	                                  FlipStepParams runs the reference's own order */
+	FLIP_SOLVER_RED_BLACK = 1,     /* red-black order (north_star's named order); bounded against the reference order (T2).
+	                                  At the reference's 50 sweeps it is less stable than the reference order on tall
+	                                  liquid columns (profiles/r1_stability.md) */
 	FLIP_SOLVER_LEX_DIAGONAL = 2,  /* same order, unblocked one-diagonal-per-grid-sync kernel (cross-check / non-binary s) */
 	FLIP_SOLVER_LEX_STRIPS = 3     /* same order, streaming skewed tile columns instead of square tiles (experimental, slower in r1) */
 } FlipSolverOrder;
@@ -106,6 +109,11 @@ int flip_get_dims(FlipSim* sim, FlipDims* dims);
 int flip_set_num_particles(FlipSim* sim, int n);
 /* host -> device, reference layout; count = number of elements (not bytes) and must match the field */
 int flip_upload(FlipSim* sim, int field, const void* host, size_t count);
+/* the per-frame form (flip_fluid/src/main.cpp:106-122 rewrites s, u, v every drag frame): the copy is only QUEUED on the handle's
+ * stream.  `host` must stay unchanged until the next synchronising call (flip_synchronize, flip_readback, flip_readback_wait),
+ * unless it is pageable memory, which the CUDA runtime stages before it returns.  Whether an uploaded s is 0/1-valued (the
+ * blocked solvers need to know) is checked on the device behind the copy. */
+int flip_upload_async(FlipSim* sim, int field, const void* host, size_t count);
 /* device -> host, reference layout and particle index order */
 int flip_readback(FlipSim* sim, int field, void* host, size_t count);
 /* particle_pos (caller order) -> pinned host memory without blocking: the PCIe copy runs on its own stream while the next

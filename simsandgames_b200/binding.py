@@ -15,8 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-RED_BLACK = 0
-LEX_WAVEFRONT = 1
+LEX_WAVEFRONT = 0   # FlipSolverOrder of include/flipgpu.h: 0 = the reference order
+RED_BLACK = 1
 LEX_DIAGONAL = 2
 LEX_STRIPS = 3
 
@@ -70,7 +70,7 @@ def lib_path():
 
 def build_library(verbose=False):
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> simsandgames_b200/libflipgpu.so (in-tree)."""
-    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=not verbose, text=True)
+    r = subprocess.run(["make", "-j8", "-C", os.path.join(_HERE, "csrc")], capture_output=not verbose, text=True)
     if r.returncode != 0:
         raise FlipGpuError("building libflipgpu.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
 
@@ -170,6 +170,11 @@ class FlipFluidGPU:
     def upload_from(self, name, ptr, count):
         fid, _ = FLIP_FIELDS[name]
         _check(self._lib.flip_upload(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"flip_upload({name})")
+
+    def upload_from_async(self, name, ptr, count):
+        """flip_upload_async: the copy is only queued; the (pinned) host buffer must stay unchanged until the next sync"""
+        fid, _ = FLIP_FIELDS[name]
+        _check(self._lib.flip_upload_async(self._h, fid, C.c_void_p(ptr), C.c_size_t(count)), f"flip_upload_async({name})")
 
     def readback_pos_async(self, ptr, count):
         """particle_pos -> (pinned) host pointer on the copy stream; returns at once, join with readback_wait()."""

@@ -36,14 +36,22 @@ void set_error(const char* fmt, ...);
 // cell types of flip_fluid.h:30-34
 enum : int { FLUID_CELL = 0, AIR_CELL = 1, SOLID_CELL = 2 };
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (148 on B200), queried once
+inline int num_sms() {
+	static int n = 0;
+	if (n == 0) {
+		int dev = 0;
+		if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+	}
+	return n;
+}
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-// Grid size for grid-stride kernels: whole waves of the 148 SMs, capped by the work available.
+// Grid size for grid-stride kernels: whole waves of the SMs, capped by the work available.
 inline unsigned wave_grid(size_t work_items, int threads, int ctas_per_sm = 8) {
 	size_t need = (work_items + threads - 1) / threads;
-	size_t full = (size_t)kNumSMs * ctas_per_sm;
+	size_t full = (size_t)num_sms() * ctas_per_sm;
 	if (need >= full) return (unsigned)full;
 	return (unsigned)(need ? need : 1);
 }
@@ -72,6 +80,7 @@ struct SorGrid {
 struct SorWorkspace;  // plan + per-cell constants of the blocked-wavefront solver (sor_tiled.cu)
 void sor_workspace_free(SorWorkspace* w);
 int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]);
+int sor_workspace_check(SorWorkspace* w);  // after a stream sync: FLIPGPU_ESTATE if a solver dependency wait timed out
 int sor_solve_tiled(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
                     LaunchCounter* lc);
 int sor_solve_strips(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,

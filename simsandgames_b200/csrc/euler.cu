@@ -304,7 +304,7 @@ int euler_readback(EulerSim* e, int field, void* host, size_t count) {
 	if (field == EULER_SOLID) FG_CUDA(cudaMemcpyAsync(host, e->solid, count, cudaMemcpyDeviceToHost, e->st));
 	else FG_CUDA(cudaMemcpyAsync(host, *efield(e, field), count * 4, cudaMemcpyDeviceToHost, e->st));
 	FG_CUDA(cudaStreamSynchronize(e->st));
-	return FLIPGPU_OK;
+	return sor_workspace_check(e->ws);
 }
 
 int euler_project(EulerSim* e, int iters, float dt, int order) {
@@ -386,7 +386,7 @@ int euler_synchronize(EulerSim* e) {
 	FG_CHECK(e, FLIPGPU_EINVAL, "null handle");
 	EDeviceGuard guard(e->device);
 	FG_CUDA(cudaStreamSynchronize(e->st));
-	return FLIPGPU_OK;
+	return sor_workspace_check(e->ws);
 }
 int euler_get_stream(EulerSim* e, void** stream) {
 	FG_CHECK(e && stream, FLIPGPU_EINVAL, "null argument");

@@ -403,6 +403,18 @@ __global__ void __launch_bounds__(kThreads) k_cell_type_from_s(int n, const floa
 		cell_type[c] = s[c] == 0.f ? SOLID_CELL : AIR_CELL;
 }
 
+// Is every s value 0 or 1?  The blocked solvers pack s into one bit per neighbour, which is exact only then; any other
+// value raises the flag and the solve takes the general kernels.  Runs behind every write of s that can introduce such
+// values (flip_upload / flip_upload_rows), on the device: no host scan, no host sync on the upload path.
+__global__ void __launch_bounds__(kThreads) k_check_s_binary(size_t n, const float* __restrict__ s, int* __restrict__ flag) {
+	bool bad = false;
+	for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+		float v = s[c];
+		bad |= !(v == 0.f || v == 1.f);
+	}
+	if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;  // racing writers store the same value
+}
+
 // ------------------------------------------------------------------ F4 + F5 marking
 // handleParticleCollisions (flip_fluid.h:254-289) fused with the fluid-cell marking of :352-359 and with
 // the key + histogram of the second (index-only) counting sort: particles by the BASE CELL (x0,y0) of their
@@ -924,10 +936,18 @@ struct FlipSim {
 	float* d_partials = nullptr;
 	float* h_pinned = nullptr;  // [0] rest mirror
 	// asynchronous readback of particle_pos (render thread consumes frame k while frame k+1 is computed)
-	cudaStream_t st_copy = nullptr;
-	cudaEvent_t ev_staged = nullptr, ev_copied = nullptr;
-	float2* staging = nullptr;
-	bool copy_pending = false;
+	// Frame pipeline.  Once the caller has asked for a frame, every flip_step un-permutes the positions into a staging buffer
+	// (caller order) on a second stream as soon as they are final -- right after the collision pass, i.e. while P2G, the
+	// pressure solve and G2P are still running -- and flip_readback_pos_async only queues the PCIe copy, on a third stream.
+	// Two staging buffers: frame k+1 is staged while frame k is still crossing PCIe.
+	cudaStream_t st_copy = nullptr, st_scatter = nullptr;
+	cudaEvent_t ev_pos_final = nullptr, ev_staged[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	float2* staging[2] = {nullptr, nullptr};
+	bool copy_pending[2] = {false, false};
+	bool frame_mode = false;     // set by the first flip_readback_pos_async
+	bool staged_valid = false;   // staging[frame_idx] holds the caller-order positions of the current state
+	bool staged_unjoined = false;  // the simulation stream has not yet been ordered behind the last staging pass
+	int frame_idx = 0;
 	SorWorkspace* ws = nullptr;
 	// slab sharding (flip_create_sharded): rank owns grid rows [j0, j1); arrays keep the global size, only the window is processed
 	bool sharded = false;
@@ -942,7 +962,11 @@ struct FlipSim {
 	int* h_counters = nullptr;   // pinned mirror
 	int n_owned = 0;
 	long long exchanges = 0;
-	bool s_binary = true;       // every s[] is 0 or 1 (tracked on upload)
+	bool s_binary = true;       // every s[] is 0 or 1 (checked on the device behind every upload of s)
+	bool s_check_pending = false;
+	int* d_sflag = nullptr;     // device: set by k_check_s_binary
+	int* h_sflag = nullptr;     // pinned mirror, valid once ev_scheck has completed
+	cudaEvent_t ev_scheck = nullptr;
 	bool exact_order = false;   // flip_set_exact_order: reference order of every float reduction (parity runs)
 	int *lvl[2] = {nullptr, nullptr}, *d_flags = nullptr;  // level schedule of the serial-order separation
 	int sep_levels = 0;
@@ -991,9 +1015,38 @@ int ensure_cell_colors(FlipSim* f) {
 	return FLIPGPU_OK;
 }
 
+// ---- frame pipeline (see FlipSim).  stage_positions: caller-order copy of the CURRENT positions into the next staging buffer,
+// on the scatter stream, ordered behind everything queued on the simulation stream so far.
+int stage_positions(FlipSim* f) {
+	const int np = f->d.num_particles;
+	if (np == 0) return FLIPGPU_OK;
+	const int b = 1 - f->frame_idx;
+	if (!f->staging[b]) FG_CUDA(cudaMalloc(&f->staging[b], (size_t)std::max(f->d.max_particles, 1) * sizeof(float2)));
+	FG_CUDA(cudaEventRecord(f->ev_pos_final, f->st));
+	FG_CUDA(cudaStreamWaitEvent(f->st_scatter, f->ev_pos_final, 0));
+	if (f->copy_pending[b]) FG_CUDA(cudaStreamWaitEvent(f->st_scatter, f->ev_copied[b], 0));  // that buffer is still crossing PCIe
+	if (f->identity) FG_CUDA(cudaMemcpyAsync(f->staging[b], f->pos[f->cur], (size_t)np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st_scatter));
+	else { k_scatter_to_caller<float2, 1><<<pgrid(f), kThreads, 0, f->st_scatter>>>(np, f->orig[f->cur], f->pos[f->cur], f->staging[b]); f->lc.n++; }
+	FG_CUDA(cudaGetLastError());
+	FG_CUDA(cudaEventRecord(f->ev_staged[b], f->st_scatter));
+	f->frame_idx = b;
+	f->staged_valid = true;
+	f->staged_unjoined = true;
+	return FLIPGPU_OK;
+}
+// Call before anything on the simulation stream writes positions / slot order: the staging pass must have read them first,
+// and the staged frame no longer matches the state afterwards.
+int positions_will_change(FlipSim* f) {
+	if (f->staged_unjoined) FG_CUDA(cudaStreamWaitEvent(f->st, f->ev_staged[f->frame_idx], 0));
+	f->staged_unjoined = false;
+	f->staged_valid = false;
+	return FLIPGPU_OK;
+}
+
 // put every particle array back into caller order (slot k == caller particle k)
 int unsort(FlipSim* f) {
 	if (f->identity) return FLIPGPU_OK;
+	FG_TRY(positions_will_change(f));
 	int np = f->d.num_particles, c = f->cur, n = 1 - c;
 	if (np > 0) {
 		unsigned gr = pgrid(f);
@@ -1064,6 +1117,7 @@ int bin_from_histogram(FlipSim* f) {
 
 int integrate_and_bin(FlipSim* f, bool integrate, bool bin, float dt, float gravity) {
 	Geo g = geo(f);
+	FG_TRY(positions_will_change(f));
 	int c = f->cur;
 	if (bin) FG_CUDA(cudaMemsetAsync(f->count + (size_t)g.pnx * g.hy0, 0, (size_t)g.pnx * (g.hy1 - g.hy0) * 4, f->st));
 	if (g.np > 0) {
@@ -1131,6 +1185,7 @@ int separate_exact(FlipSim* f, int iters, bool colors) {
 int separate(FlipSim* f, int iters, bool colors) {
 	Geo g = geo(f);
 	if (g.np == 0) return FLIPGPU_OK;
+	FG_TRY(positions_will_change(f));
 	if (f->exact_order) return separate_exact(f, iters, colors);
 	if (colors) FG_TRY(ensure_colors(f));
 	// Sweeps ping-pong between the two position buffers; velocities (and ids) stay in buffer `cur`,
@@ -1157,6 +1212,7 @@ int separate(FlipSim* f, int iters, bool colors) {
 
 int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad) {
 	Geo g = geo(f);
+	if (collide) FG_TRY(positions_will_change(f));
 	const size_t goff = (size_t)g.nx * g.gy0;
 	int c = f->cur, C = g.nx * (g.gy1 - g.gy0);
 	if (mark) {
@@ -1236,8 +1292,32 @@ int ensure_alt(FlipSim* f) {
 	FG_CUDA(cudaMemsetAsync(f->u_alt, 0, C * 4, f->st)); FG_CUDA(cudaMemsetAsync(f->v_alt, 0, C * 4, f->st)); FG_CUDA(cudaMemsetAsync(f->p_alt, 0, C * 4, f->st));
 	return FLIPGPU_OK;
 }
+// s was written by the caller: check on the device (asynchronously) whether it is still 0/1-valued
+int queue_s_check(FlipSim* f, size_t first_cell, size_t n_cells, bool whole_array) {
+	if (n_cells == 0) return FLIPGPU_OK;
+	// a whole-array upload starts from scratch; a partial one adds to what is known (or still being checked) about the rest
+	if (whole_array) FG_CUDA(cudaMemsetAsync(f->d_sflag, 0, sizeof(int), f->st));
+	else if (!f->s_check_pending) FG_CUDA(cudaMemsetAsync(f->d_sflag, f->s_binary ? 0 : 0xff, sizeof(int), f->st));
+	k_check_s_binary<<<wave_grid(n_cells, kThreads), kThreads, 0, f->st>>>(n_cells, f->s + first_cell, f->d_sflag);
+	f->lc.n++;
+	FG_CUDA(cudaGetLastError());
+	FG_CUDA(cudaMemcpyAsync(f->h_sflag, f->d_sflag, sizeof(int), cudaMemcpyDeviceToHost, f->st));
+	FG_CUDA(cudaEventRecord(f->ev_scheck, f->st));
+	f->s_check_pending = true;
+	return FLIPGPU_OK;
+}
+// ... and wait for the answer only where the solver is chosen (the upload and the check are long done by then)
+int resolve_s_binary(FlipSim* f) {
+	if (!f->s_check_pending) return FLIPGPU_OK;
+	FG_CUDA(cudaEventSynchronize(f->ev_scheck));
+	f->s_binary = *f->h_sflag == 0;
+	f->s_check_pending = false;
+	return FLIPGPU_OK;
+}
+
 // the projection of one step; an odd number of ping-pong rounds leaves the result in the partner arrays -> swap the names
 int solve(FlipSim* f, int iters, float cp, float omega, bool drift, int order) {
+	FG_TRY(resolve_s_binary(f));
 	if (order == FLIP_SOLVER_RED_BLACK && f->s_binary) FG_TRY(ensure_alt(f));
 	bool swapped = false;
 	FG_TRY(sor_solve(&f->ws, sor_view(f), iters, cp, omega, drift, order, f->s_binary, f->st, &f->lc, &swapped));
@@ -1368,6 +1448,7 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 int shard_solve(FlipSim* f, int iters, float cp, float omega, bool drift) {
 	const int H = f->halo, K = std::max(H - 1, 1), ny = f->d.f_num_y;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
+	FG_TRY(resolve_s_binary(f));  // (both branches below issue the same NCCL exchanges, so ranks may differ in this)
 	if (f->s_binary && K == sor_rb_passes_per_round()) {
 		FG_TRY(ensure_alt(f));
 		FG_TRY(sor_rb_prep(&f->ws, sor_view(f), drift, f->gy0, f->gy1, f->st, &f->lc));
@@ -1530,8 +1611,12 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	d.num_particles = 0;
 	FG_CUDA(cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking));
 	FG_CUDA(cudaStreamCreateWithFlags(&f->st_copy, cudaStreamNonBlocking));
-	FG_CUDA(cudaEventCreateWithFlags(&f->ev_staged, cudaEventDisableTiming));
-	FG_CUDA(cudaEventCreateWithFlags(&f->ev_copied, cudaEventDisableTiming));
+	FG_CUDA(cudaStreamCreateWithFlags(&f->st_scatter, cudaStreamNonBlocking));
+	FG_CUDA(cudaEventCreateWithFlags(&f->ev_pos_final, cudaEventDisableTiming));
+	for (int b = 0; b < 2; b++) {
+		FG_CUDA(cudaEventCreateWithFlags(&f->ev_staged[b], cudaEventDisableTiming));
+		FG_CUDA(cudaEventCreateWithFlags(&f->ev_copied[b], cudaEventDisableTiming));
+	}
 	size_t C = d.f_num_cells, M = std::max(d.max_particles, 1), H = d.p_num_cells;
 	float** grids[] = {&f->u, &f->v, &f->prev_u, &f->prev_v, &f->p, &f->s, &f->dens};
 	for (float** gp : grids) {
@@ -1563,6 +1648,10 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	FG_CUDA(cudaMalloc(&f->d_partials, (3 * kPartials + 8) * 4));
 	FG_CUDA(cudaMallocHost(&f->h_pinned, 64));
 	f->h_pinned[0] = 0.f;
+	FG_CUDA(cudaMalloc(&f->d_sflag, sizeof(int)));
+	FG_CUDA(cudaMallocHost(&f->h_sflag, sizeof(int)));
+	*f->h_sflag = 0;
+	FG_CUDA(cudaEventCreateWithFlags(&f->ev_scheck, cudaEventDisableTiming));
 	for (int r = 0; r < FlipSim::kEvRing; r++)
 		for (int i = 0; i <= FLIP_PH_COUNT; i++) FG_CUDA(cudaEventCreate(&f->ev[r][i]));
 	FG_CUDA(cudaStreamSynchronize(f->st));
@@ -1584,10 +1673,17 @@ int flip_destroy(FlipSim* f) {
 	cudaFree(f->lvl[0]); cudaFree(f->lvl[1]); cudaFree(f->d_flags);
 	if (f->h_counters) cudaFreeHost(f->h_counters);
 	if (f->h_pinned) cudaFreeHost(f->h_pinned);
+	cudaFree(f->d_sflag);
+	if (f->h_sflag) cudaFreeHost(f->h_sflag);
+	if (f->ev_scheck) cudaEventDestroy(f->ev_scheck);
+	if (f->st_scatter) { cudaStreamSynchronize(f->st_scatter); cudaStreamDestroy(f->st_scatter); }
 	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
-	if (f->ev_staged) cudaEventDestroy(f->ev_staged);
-	if (f->ev_copied) cudaEventDestroy(f->ev_copied);
-	if (f->staging) cudaFree(f->staging);
+	if (f->ev_pos_final) cudaEventDestroy(f->ev_pos_final);
+	for (int b = 0; b < 2; b++) {
+		if (f->ev_staged[b]) cudaEventDestroy(f->ev_staged[b]);
+		if (f->ev_copied[b]) cudaEventDestroy(f->ev_copied[b]);
+		if (f->staging[b]) cudaFree(f->staging[b]);
+	}
 	sor_workspace_free(f->ws);
 	for (int r = 0; r < FlipSim::kEvRing; r++)
 		for (int i = 0; i <= FLIP_PH_COUNT; i++) if (f->ev[r][i]) cudaEventDestroy(f->ev[r][i]);
@@ -1608,12 +1704,13 @@ int flip_set_num_particles(FlipSim* f, int n) {
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "sharded simulation: the particle count follows flip_upload_particles");
 	DeviceGuard guard(f->device);
 	FG_TRY(unsort(f));
+	FG_TRY(positions_will_change(f));
 	f->d.num_particles = n;
 	f->bins_valid = false;
 	return FLIPGPU_OK;
 }
 
-int flip_upload(FlipSim* f, int field, const void* host, size_t count) {
+static int upload_impl(FlipSim* f, int field, const void* host, size_t count, bool wait) {
 	FG_CHECK(f && host, FLIPGPU_EINVAL, "flip_upload: null argument");
 	FG_CHECK(field >= 0 && field < FLIP_FIELD_COUNT, FLIPGPU_EINVAL, "flip_upload: unknown field %d", field);
 	DeviceGuard guard(f->device);
@@ -1623,7 +1720,7 @@ int flip_upload(FlipSim* f, int field, const void* host, size_t count) {
 	FG_CHECK(dst || !f->sharded, FLIPGPU_ESTATE, "sharded simulation: use flip_upload_particles / flip_upload_rows");
 	if (!dst) {
 		switch (field) {
-			case FLIP_PARTICLE_POS: FG_TRY(unsort(f)); dst = f->pos[f->cur]; f->bins_valid = false; break;
+			case FLIP_PARTICLE_POS: FG_TRY(unsort(f)); FG_TRY(positions_will_change(f)); dst = f->pos[f->cur]; f->bins_valid = false; break;
 			case FLIP_PARTICLE_VEL: FG_TRY(unsort(f)); dst = f->vel[f->cur]; break;
 			case FLIP_PARTICLE_COLOR: FG_TRY(ensure_colors(f)); FG_TRY(unsort(f)); dst = f->col[f->cur]; break;
 			case FLIP_CELL_COLOR: FG_TRY(ensure_cell_colors(f)); dst = f->cell_color; break;
@@ -1632,16 +1729,17 @@ int flip_upload(FlipSim* f, int field, const void* host, size_t count) {
 				return FLIPGPU_EINVAL;
 		}
 	}
-	if (field == FLIP_S) {  // the blocked solver packs s into one bit per neighbour; remember whether that is exact
-		const float* hs = (const float*)host;
-		bool bin = true;
-		for (size_t i = 0; i < count && bin; i++) bin = hs[i] == 0.f || hs[i] == 1.f;
-		f->s_binary = bin;
-	}
 	if (count) FG_CUDA(cudaMemcpyAsync(dst, host, count * 4, cudaMemcpyHostToDevice, f->st));
-	FG_CUDA(cudaStreamSynchronize(f->st));
+	// the blocked solvers pack s into one bit per neighbour; whether that is exact is checked on the device, behind the copy
+	if (field == FLIP_S) FG_TRY(queue_s_check(f, 0, count, true));
+	if (wait) FG_CUDA(cudaStreamSynchronize(f->st));
 	return FLIPGPU_OK;
 }
+int flip_upload(FlipSim* f, int field, const void* host, size_t count) { return upload_impl(f, field, host, count, true); }
+// The per-frame form (main.cpp:106-122 rewrites s, u, v every drag frame): the copy is only queued on the handle's stream.
+// `host` must stay unchanged until the next synchronising call (flip_synchronize, flip_readback*, flip_readback_wait) unless it is
+// pageable memory, which the CUDA runtime stages before returning.
+int flip_upload_async(FlipSim* f, int field, const void* host, size_t count) { return upload_impl(f, field, host, count, false); }
 
 int flip_readback(FlipSim* f, int field, void* host, size_t count) {
 	FG_CHECK(f && host, FLIPGPU_EINVAL, "flip_readback: null argument");
@@ -1681,36 +1779,37 @@ int flip_readback(FlipSim* f, int field, void* host, size_t count) {
 	FG_CUDA(cudaGetLastError());
 	if (count) FG_CUDA(cudaMemcpyAsync(host, srcp, count * 4, cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
-	return FLIPGPU_OK;
+	return sor_workspace_check(f->ws);
 }
 
-// particle_pos in caller order -> host, without blocking the caller or the simulation stream: the un-permute runs on
-// the simulation stream into a staging buffer, the PCIe copy on a second stream; flip_readback_wait() joins it.
+// particle_pos in caller order -> host, without blocking the caller or the simulation stream (frame pipeline, see FlipSim).
+// If the last flip_step already staged this state only the PCIe copy is queued here; otherwise the un-permute runs now.
 int flip_readback_pos_async(FlipSim* f, void* host, size_t count) {
 	FG_CHECK(f && host, FLIPGPU_EINVAL, "flip_readback_pos_async: null argument");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "sharded simulation: slots carry GLOBAL particle indices, use flip_readback_particles");
 	FG_CHECK(count == 2 * (size_t)f->d.num_particles, FLIPGPU_EINVAL, "flip_readback_pos_async: particle_pos holds %zu elements, asked for %zu",
 	         2 * (size_t)f->d.num_particles, count);
 	DeviceGuard guard(f->device);
-	int np = f->d.num_particles;
-	if (np == 0) return FLIPGPU_OK;
-	if (!f->staging) FG_CUDA(cudaMalloc(&f->staging, (size_t)std::max(f->d.max_particles, 1) * sizeof(float2)));
-	if (f->copy_pending) FG_CUDA(cudaStreamWaitEvent(f->st, f->ev_copied, 0));  // the staging buffer is still being read
-	if (f->identity) FG_CUDA(cudaMemcpyAsync(f->staging, f->pos[f->cur], (size_t)np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st));
-	else { k_scatter_to_caller<float2, 1><<<pgrid(f), kThreads, 0, f->st>>>(np, f->orig[f->cur], f->pos[f->cur], f->staging); f->lc.n++; }
-	FG_CUDA(cudaGetLastError());
-	FG_CUDA(cudaEventRecord(f->ev_staged, f->st));
-	FG_CUDA(cudaStreamWaitEvent(f->st_copy, f->ev_staged, 0));
-	FG_CUDA(cudaMemcpyAsync(host, f->staging, count * 4, cudaMemcpyDeviceToHost, f->st_copy));
-	FG_CUDA(cudaEventRecord(f->ev_copied, f->st_copy));
-	f->copy_pending = true;
+	f->frame_mode = true;
+	if (f->d.num_particles == 0) return FLIPGPU_OK;
+	if (!f->staged_valid) FG_TRY(stage_positions(f));
+	const int b = f->frame_idx;
+	FG_CUDA(cudaStreamWaitEvent(f->st_copy, f->ev_staged[b], 0));
+	FG_CUDA(cudaMemcpyAsync(host, f->staging[b], count * 4, cudaMemcpyDeviceToHost, f->st_copy));
+	FG_CUDA(cudaEventRecord(f->ev_copied[b], f->st_copy));
+	f->copy_pending[b] = true;
 	return FLIPGPU_OK;
 }
 int flip_readback_wait(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	DeviceGuard guard(f->device);
-	if (f->copy_pending) FG_CUDA(cudaEventSynchronize(f->ev_copied));
-	f->copy_pending = false;
-	return FLIPGPU_OK;
+	for (int b = 0; b < 2; b++) {
+		if (f->copy_pending[b]) FG_CUDA(cudaEventSynchronize(f->ev_copied[b]));
+		f->copy_pending[b] = false;
+	}
+	// The frame is complete on the host.  The step that produced it may still be running its solve (the positions are final
+	// before it): a solver time-out of that step is reported by the next call that synchronises the simulation stream.
+	return sor_workspace_check(f->ws);
 }
 
 int flip_set_obstacle(FlipSim* f, float x, float y, float vx, float vy, float radius) {
@@ -1745,6 +1844,8 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0));
 		phase_mark(f, FLIP_PH_COLLIDE_MARK);
 		FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
+		// the positions of this step are final: in frame mode their caller-order copy is made now, beside P2G / solve / G2P
+		if (f->frame_mode && k == n_steps - 1) FG_TRY(stage_positions(f));
 		phase_mark(f, FLIP_PH_P2G);
 		FG_TRY(p2g(f));
 		phase_mark(f, FLIP_PH_SOLVE);
@@ -1869,8 +1970,10 @@ static int rows_copy(FlipSim* f, int field, void* host, int j_start, int n_rows,
 	if (bytes) {
 		if (to_device) FG_CUDA(cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, f->st));
 		else FG_CUDA(cudaMemcpyAsync(host, base + off, bytes, cudaMemcpyDeviceToHost, f->st));
+		if (to_device && field == FLIP_S) FG_TRY(queue_s_check(f, (size_t)j_start * f->d.f_num_x, (size_t)n_rows * f->d.f_num_x, false));
 	}
 	FG_CUDA(cudaStreamSynchronize(f->st));
+	if (!to_device) FG_TRY(sor_workspace_check(f->ws));
 	return FLIPGPU_OK;
 }
 int flip_upload_rows(FlipSim* f, int field, const void* host, int j_start, int n_rows) { return rows_copy(f, field, const_cast<void*>(host), j_start, n_rows, true); }
@@ -1878,27 +1981,32 @@ int flip_readback_rows(FlipSim* f, int field, void* host, int j_start, int n_row
 
 int flip_phase_integrate(FlipSim* f, float dt, float gravity) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	return integrate_and_bin(f, true, false, dt, gravity);
 }
 int flip_phase_bin(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	return integrate_and_bin(f, false, true, 0.f, 0.f);
 }
 int flip_phase_separate(FlipSim* f, int num_iters, int update_colors) {
 	FG_CHECK(f && num_iters >= 0, FLIPGPU_EINVAL, "flip_phase_separate: bad argument");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	if (!f->bins_valid) FG_TRY(integrate_and_bin(f, false, true, 0.f, 0.f));
 	return separate(f, num_iters, update_colors != 0);
 }
 int flip_phase_collide(FlipSim* f, float ox, float oy, float ovx, float ovy, float orad) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	return collide_mark(f, true, false, ox, oy, ovx, ovy, orad);
 }
 int flip_phase_p2g(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
 	FG_TRY(collide_mark(f, false, true, 0, 0, 0, 0, 0));
@@ -1906,6 +2014,7 @@ int flip_phase_p2g(FlipSim* f) {
 }
 int flip_phase_solve(FlipSim* f, int iters, float dt, float omega, int drift, int order) {
 	FG_CHECK(f && dt > 0 && iters >= 0, FLIPGPU_EINVAL, "flip_phase_solve: bad argument");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	// :452-454
 	FG_CUDA(cudaMemsetAsync(f->p, 0, (size_t)f->d.f_num_cells * 4, f->st));
@@ -1915,11 +2024,13 @@ int flip_phase_solve(FlipSim* f, int iters, float dt, float omega, int drift, in
 }
 int flip_phase_g2p(FlipSim* f, float flip_ratio) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	return g2p(f, flip_ratio);
 }
 int flip_phase_colors(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
 	return colors(f);
 }
@@ -1975,7 +2086,7 @@ int flip_synchronize(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	DeviceGuard guard(f->device);
 	FG_CUDA(cudaStreamSynchronize(f->st));
-	return FLIPGPU_OK;
+	return sor_workspace_check(f->ws);  // FLIPGPU_ESTATE if a solver dependency wait timed out since the last check
 }
 int flip_get_stream(FlipSim* f, void** stream) {
 	FG_CHECK(f && stream, FLIPGPU_EINVAL, "null argument");

@@ -47,21 +47,18 @@ struct TiledArgs {
 	int epoch;
 	float cp, omega;
 	unsigned long long* prof;  // [0] wait [1] load [2] compute [3] write-back cycles (thread 0 of every CTA), [4] tiles
+	int* status;               // device error word: a dependency wait that timed out stores FLIPGPU_ESTATE here
 };
-
-__device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
-	for (long long spins = 0; *((volatile const int*)flag) != epoch && spins < (1ll << 25); spins++) __nanosleep(64);
-}
 
 // ceil(2^16 / d): floor(n / d) == (n * magic[d]) >> 16 for every n < 1024, d <= 32 (checked exhaustively)
 __constant__ unsigned c_div_magic[33] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554,
                                          5958,  5462,  5042,  4682,  4370,  4096,  3856,  3641, 3450, 3277, 3121,
                                          2979,  2850,  2731,  2622,  2521,  2428,  2341,  2260, 2185, 2115, 2048};
 
-// V2 (opt-in, FLIPGPU_SOR_V2=1; same work items, same arithmetic, same results): the per-step item decode is two integer
-// instructions instead of an fp32 reciprocal + conversions, and every operand of the cell is fetched in ONE shared-memory
-// round trip (the baseline SASS tests the cell code first and only then loads the operands).
-template <bool XFAST, bool DRIFT, int KW, bool V2>  // KW warps per CTA (>= iterations per chunk)
+// The per-step item decode is a multiply-shift by a constant-bank magic number, every operand of a cell is fetched in ONE
+// shared-memory round trip, and the per-solve planes (cell code, drift term) plus the activity map are fetched before the
+// predecessor flags are awaited (r2 A/B on B200, profiles/r2_ab_v2_variants_4096.jsonl: 5.19 -> 4.46 ms at S2, bit-identical).
+template <bool XFAST, bool DRIFT, int KW>  // KW warps per CTA (>= iterations per chunk)
 __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_kernel(TiledArgs A) {
 	// dynamic shared memory (> 48 KB with the drift term): four float planes and the cell code as a 32-bit word per cell
 	// (a byte plane would put several lanes of a diagonal into one bank)
@@ -72,6 +69,7 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 	unsigned* s_code = reinterpret_cast<unsigned*>(s_p + kBoxW * kBoxW);
 	float* s_dr = reinterpret_cast<float*>(s_code + kBoxW * kBoxW);  // only touched when DRIFT
 	__shared__ int s_tile;
+	__shared__ int s_ok;
 	const int tid = threadIdx.y * kTile + threadIdx.x;
 	const int nthreads = kTile * blockDim.y;
 	const int nf = A.nf, ns = A.ns;
@@ -84,20 +82,22 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		const int4 tl = A.tiles[ti];
 		const int I = tl.x, J = tl.y, q = tl.z, kq = tl.w;
 		long long c0 = clock64();
-		// V2: the activity of the tile's squares does not depend on the predecessors -- fetch it while waiting for them
-		bool any_pre = false;
-		if (V2)
-			for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
-				for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any_pre |= A.act[jj * A.na + ii] != 0;
-		if (V2 && any_pre) {  // ... and so are the per-solve cell constants: stage the code / drift planes of the box now
-			const int FBp = 1 + I * kTile - A.kc + 1, SBp = 1 + J * kTile - A.kc + 1;
+		// the activity of the tile's squares does not depend on the predecessors -- fetch it while waiting for them.  The skewed
+		// tile lies inside the four unskewed squares (I-1..I, J-1..J): if none of them holds an active cell (all air / solid)
+		// the tile changes nothing and is published as soon as its predecessors are done (dam-break: about half the tiles)
+		bool any = false;
+		for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
+			for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any |= A.act[jj * A.na + ii] != 0;
+		const int F0 = 1 + I * kTile, S0 = 1 + J * kTile;
+		const int FB = F0 - A.kc + 1, SB = S0 - A.kc + 1;  // box origin (cells FB..FB+kBoxW-1)
+		if (any) {  // ... and so are the per-solve cell constants: stage the code / drift planes of the box now
 			constexpr int kRoundsP = (kBoxW * kBoxW + kTile * KW - 1) / (kTile * KW);
 			unsigned p_cd[kRoundsP];
 			float p_dr[kRoundsP];
 #pragma unroll
 			for (int r = 0; r < kRoundsP; r++) {
 				int e = tid + r * nthreads;
-				int F = FBp + e % kBoxW, S = SBp + e / kBoxW;
+				int F = FB + e % kBoxW, S = SB + e / kBoxW;
 				p_cd[r] = 0; p_dr[r] = 0.f;
 				if (e < kBoxW * kBoxW && F >= 0 && F < nf && S >= 0 && S < ns) {
 					size_t c = (size_t)F + (size_t)nf * S;
@@ -115,71 +115,52 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 			}
 		}
 		if (tid == 0) {
-			if (V2) {
-				// the three predecessor flags are polled together (one L2 round trip per poll instead of up to three in a row),
-				// without sleeping: one thread per CTA spins, and the tile usually sits on the critical path of the wavefront
-				const int* f1 = I > 0 ? A.flags + (q * A.nj + J) * A.ni + I - 1 : nullptr;
-				const int* f2 = J > 0 ? A.flags + (q * A.nj + J - 1) * A.ni + I : nullptr;
-				const int* f3 = q > 0 ? A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1) : nullptr;
-				for (long long spins = 0; spins < (1ll << 27); spins++) {
-					int v1 = f1 ? *((volatile const int*)f1) : A.epoch, v2 = f2 ? *((volatile const int*)f2) : A.epoch,
-					    v3 = f3 ? *((volatile const int*)f3) : A.epoch;
-					if (v1 == A.epoch && v2 == A.epoch && v3 == A.epoch) break;
-				}
-			} else {
-				if (I > 0) wait_flag(A.flags + (q * A.nj + J) * A.ni + I - 1, A.epoch);
-				if (J > 0) wait_flag(A.flags + (q * A.nj + J - 1) * A.ni + I, A.epoch);
-				if (q > 0) wait_flag(A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1), A.epoch);
+			// the three predecessor flags are polled together (one L2 round trip per poll instead of up to three in a row),
+			// without sleeping: one thread per CTA spins, and the tile usually sits on the critical path of the wavefront.
+			// The spin is bounded (~seconds); a time-out raises the solver's error word and ends the launch -- the host
+			// reports FLIPGPU_ESTATE at its next synchronising call instead of returning a stale pressure field.
+			const int* f1 = I > 0 ? A.flags + (q * A.nj + J) * A.ni + I - 1 : nullptr;
+			const int* f2 = J > 0 ? A.flags + (q * A.nj + J - 1) * A.ni + I : nullptr;
+			const int* f3 = q > 0 ? A.flags + ((q - 1) * A.nj + min(J + 1, A.nj - 1)) * A.ni + min(I + 1, A.ni - 1) : nullptr;
+			int ok = 0;
+			for (long long spins = 0; spins < (1ll << 27); spins++) {
+				int v1 = f1 ? *((volatile const int*)f1) : A.epoch, v2 = f2 ? *((volatile const int*)f2) : A.epoch,
+				    v3 = f3 ? *((volatile const int*)f3) : A.epoch;
+				if (v1 == A.epoch && v2 == A.epoch && v3 == A.epoch) { ok = 1; break; }
+				if ((spins & 1023) == 1023 && *((volatile const int*)A.status) != 0) break;  // another CTA already gave up
 			}
+			if (!ok) atomicExch(A.status, FLIPGPU_ESTATE);
+			s_ok = ok;
 			__threadfence();
 		}
 		__syncthreads();
+		if (!s_ok) return;
 		long long c1 = clock64();
-		{	// the skewed tile lies inside the four unskewed squares (I-1..I, J-1..J): if none of them holds an active
-			// cell (all air / solid) the tile changes nothing -- publish it at once (dam-break: about half the tiles)
-			bool any = any_pre;
-			if (!V2)
-				for (int jj = max(J - 1, 0); jj <= min(J, A.nb - 1); jj++)
-					for (int ii = max(I - 1, 0); ii <= min(I, A.na - 1); ii++) any |= A.act[jj * A.na + ii] != 0;
-			if (!any) {
-				if (tid == 0) *((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
-				continue;
-			}
+		if (!any) {
+			if (tid == 0) *((volatile int*)(A.flags + (q * A.nj + J) * A.ni + I)) = A.epoch;
+			continue;
 		}
-		const int F0 = 1 + I * kTile, S0 = 1 + J * kTile;
-		const int FB = F0 - A.kc + 1, SB = S0 - A.kc + 1;  // box origin (cells FB..FB+kBoxW-1)
 		// ---- stage the box (L2-coherent loads: the producers are other CTAs of this launch).  All loads of a thread are
 		// issued before any is consumed, so the box costs one L2 round trip instead of one per element: the tile sits on
 		// the critical path of the wavefront and its fixed costs are paid once per wave.
 		{
 			constexpr int kRounds = (kBoxW * kBoxW + kTile * KW - 1) / (kTile * KW);
-			float r_vf[kRounds], r_vs[kRounds], r_p[kRounds], r_dr[kRounds];
-			unsigned r_cd[kRounds];
+			float r_vf[kRounds], r_vs[kRounds], r_p[kRounds];
 #pragma unroll
 			for (int r = 0; r < kRounds; r++) {
 				int e = tid + r * nthreads;
 				int lf = e % kBoxW, ls = e / kBoxW;
 				int F = FB + lf, S = SB + ls;
-				r_vf[r] = 0.f; r_vs[r] = 0.f; r_p[r] = 0.f; r_dr[r] = 0.f; r_cd[r] = 0;
+				r_vf[r] = 0.f; r_vs[r] = 0.f; r_p[r] = 0.f;
 				if (e < kBoxW * kBoxW && F >= 0 && F < nf && S >= 0 && S < ns) {
 					size_t c = (size_t)F + (size_t)nf * S;
 					r_vf[r] = __ldcg(A.vel_f + c); r_vs[r] = __ldcg(A.vel_s + c); r_p[r] = __ldcg(A.p + c);
-					if (!V2) {
-						r_cd[r] = A.code[c];
-						if (DRIFT) r_dr[r] = A.drift[c];
-					}
 				}
 			}
 #pragma unroll
 			for (int r = 0; r < kRounds; r++) {
 				int e = tid + r * nthreads;
-				if (e < kBoxW * kBoxW) {
-					s_vf[e] = r_vf[r]; s_vs[e] = r_vs[r]; s_p[e] = r_p[r];
-					if (!V2) {
-						s_code[e] = r_cd[r];
-						if (DRIFT) s_dr[e] = r_dr[r];
-					}
-				}
+				if (e < kBoxW * kBoxW) { s_vf[e] = r_vf[r]; s_vs[e] = r_vs[r]; s_p[e] = r_p[r]; }
 			}
 		}
 		__syncthreads();
@@ -194,40 +175,33 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		for (int t = 0; t < 2 * kTile - 1; t++) {
 			const int alo = max(0, t - (kTile - 1)), cnt = min(kTile - 1, t) - alo + 1;
 			if (tid < cnt * kq) {
-				const int k = V2 ? (int)(((unsigned)tid * c_div_magic[cnt]) >> 16)
-				                 : (int)(((float)tid + 0.5f) * (1.f / (float)cnt));  // tid / cnt: the quotient is >= 1/64 away from an integer
+				const int k = (int)(((unsigned)tid * c_div_magic[cnt]) >> 16);  // tid / cnt
 				const int a = alo + (tid - k * cnt);
-				{
-					// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
-					int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
-					// every operand is fetched before the activity test: one shared-memory round trip per step instead of two
-					unsigned cd = s_code[e];
-					float vfc, vfp, vsc, vsp, pp, dr = 0.f;
-					if (V2) {  // volatile reads cannot be sunk below the activity test: the seven loads go out back to back
-						vfc = *(volatile float*)(s_vf + e); vfp = *(volatile float*)(s_vf + e + 1); vsc = *(volatile float*)(s_vs + e);
-						vsp = *(volatile float*)(s_vs + e + kBoxW); pp = *(volatile float*)(s_p + e);
-						if (DRIFT) dr = *(volatile float*)(s_dr + e);
+				// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
+				const int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
+				// every operand is fetched before the activity test (volatile reads cannot be sunk below it): the seven
+				// loads go out back to back, one shared-memory round trip per step instead of two
+				const unsigned cd = s_code[e];
+				const float vfc = *(volatile float*)(s_vf + e), vfp = *(volatile float*)(s_vf + e + 1), vsc = *(volatile float*)(s_vs + e),
+				            vsp = *(volatile float*)(s_vs + e + kBoxW), pp = *(volatile float*)(s_p + e);
+				float dr = 0.f;
+				if (DRIFT) dr = *(volatile float*)(s_dr + e);
+				if (cd & 1u) {
+					float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
+					if (DRIFT) div -= dr;        // the stored term is max(0, density-rest): subtracting 0 is exact
+					if (cd == 31u) {             // all four neighbours open: s_sum = 4 and x/4 == x*0.25 exactly
+						float pv = (-div * 0.25f) * A.omega;
+						s_p[e] = pp + A.cp * pv;
+						s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[e + kBoxW] = vsp + pv;
 					} else {
-						vfc = s_vf[e]; vfp = s_vf[e + 1]; vsc = s_vs[e]; vsp = s_vs[e + kBoxW]; pp = s_p[e];
-						if (DRIFT) dr = s_dr[e];
-					}
-					if (cd & 1u) {
-						float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
-						if (DRIFT) div -= dr;        // the stored term is max(0, density-rest): subtracting 0 is exact
-						if (cd == 31u) {             // all four neighbours open: s_sum = 4 and x/4 == x*0.25 exactly
-							float pv = (-div * 0.25f) * A.omega;
-							s_p[e] = pp + A.cp * pv;
-							s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[e + kBoxW] = vsp + pv;
-						} else {
-							float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
-							float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
-							float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
-							float pv = -div / ssum;
-							pv *= A.omega;
-							s_p[e] = pp + A.cp * pv;
-							s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
-							s_vs[e] = vsc - ssm * pv; s_vs[e + kBoxW] = vsp + ssp * pv;
-						}
+						float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
+						float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
+						float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
+						float pv = -div / ssum;
+						pv *= A.omega;
+						s_p[e] = pp + A.cp * pv;
+						s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
+						s_vs[e] = vsc - ssm * pv; s_vs[e + kBoxW] = vsp + ssp * pv;
 					}
 				}
 			}
@@ -306,6 +280,8 @@ struct SorWorkspace {
 	int* progress = nullptr;  // per strip: rows S < progress are final in global memory
 	int n_strips = 0;
 	int sms = 0;
+	int* status = nullptr;    // device error word raised by a dependency wait that timed out ...
+	int* h_status = nullptr;  // ... mirrored into pinned host memory behind every solve launch
 };
 
 // diagnostic: cycles spent per tile phase (enabled by FLIPGPU_SOR_PROFILE=1 in the environment at plan time)
@@ -320,7 +296,17 @@ int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]) {
 void sor_workspace_free(SorWorkspace* w) {
 	if (!w) return;
 	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter); cudaFree(w->prof); cudaFree(w->strips); cudaFree(w->progress); cudaFree(w->act);
+	cudaFree(w->status);
+	if (w->h_status) cudaFreeHost(w->h_status);
 	delete w;
+}
+
+// Call after the stream that ran the solves has been synchronised: FLIPGPU_ESTATE if an inter-CTA dependency wait of a
+// persistent solver kernel timed out (the pressure field of that solve is then incomplete).
+int sor_workspace_check(SorWorkspace* w) {
+	if (!w || !w->h_status || *w->h_status == 0) return FLIPGPU_OK;
+	fg::set_error("pressure solve: an inter-CTA dependency wait timed out (GPU preempted or oversubscribed?); the solve is incomplete");
+	return FLIPGPU_ESTATE;
 }
 
 static int ensure_cell_constants(SorWorkspace* w, const SorGrid& g) {
@@ -335,6 +321,12 @@ static int ensure_cell_constants(SorWorkspace* w, const SorGrid& g) {
 		FG_CUDA(cudaMalloc(&w->act, (size_t)w->na * w->nb));
 		w->nf = g.nf; w->ns = g.ns; w->iters = 0;
 		if (!w->counter) FG_CUDA(cudaMalloc(&w->counter, 4));
+		if (!w->status) {
+			FG_CUDA(cudaMalloc(&w->status, 4));
+			FG_CUDA(cudaMemset(w->status, 0, 4));
+			FG_CUDA(cudaMallocHost(&w->h_status, 4));
+			*w->h_status = 0;
+		}
 		if (!w->prof && getenv("FLIPGPU_SOR_PROFILE")) {
 			FG_CUDA(cudaMalloc(&w->prof, 8 * sizeof(unsigned long long)));
 			FG_CUDA(cudaMemset(w->prof, 0, 8 * sizeof(unsigned long long)));
@@ -407,17 +399,16 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
 	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega; A.prof = w->prof;
-	A.act = w->act; A.na = w->na; A.nb = w->nb;
+	A.act = w->act; A.na = w->na; A.nb = w->nb; A.status = w->status;
 	const int kw = w->kc <= 8 ? 8 : 16;  // warps per CTA: the box staging is unrolled for exactly this many threads
 	dim3 block(kTile, kw);
 	int per_sm = 0;
 	const void* fn;
-	static const bool v2 = getenv("FLIPGPU_SOR_V2") && atoi(getenv("FLIPGPU_SOR_V2")) != 0;  // opt-in until validated on hardware
-#define FG_TILED_FN(KWV, V2V)                                                                                                          \
-	(g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, KWV, V2V> : (const void*)sor_gs_tiled_kernel<true, false, KWV, V2V>) \
-	          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, KWV, V2V> : (const void*)sor_gs_tiled_kernel<false, false, KWV, V2V>))
-	if (kw == 8) fn = v2 ? FG_TILED_FN(8, true) : FG_TILED_FN(8, false);
-	else fn = v2 ? FG_TILED_FN(16, true) : FG_TILED_FN(16, false);
+#define FG_TILED_FN(KWV)                                                                                                          \
+	(g.x_fast ? (use_drift ? (const void*)sor_gs_tiled_kernel<true, true, KWV> : (const void*)sor_gs_tiled_kernel<true, false, KWV>) \
+	          : (use_drift ? (const void*)sor_gs_tiled_kernel<false, true, KWV> : (const void*)sor_gs_tiled_kernel<false, false, KWV>))
+	if (kw == 8) fn = FG_TILED_FN(8);
+	else fn = FG_TILED_FN(16);
 #undef FG_TILED_FN
 	const size_t tile_smem = (size_t)kBoxW * kBoxW * 4 * (use_drift ? 5 : 4);
 	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
@@ -426,6 +417,7 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	int blocks = std::min(w->n_tiles, std::max(1, per_sm) * w->sms);
 	void* args[] = {&A};
 	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, tile_smem, st));
+	FG_CUDA(cudaMemcpyAsync(w->h_status, w->status, 4, cudaMemcpyDeviceToHost, st));
 	if (lc) lc->n += 2;
 	return FLIPGPU_OK;
 }
@@ -457,10 +449,7 @@ struct RbArgs {
 	float cp, omega;
 };
 
-// V2 (opt-in, FLIPGPU_RB_V2=1; same cells, same arithmetic, same results): a thread's (up to five) cells of one colour pass
-// never share a face, so their codes are fetched together, then the operands of the active ones together, and only then the
-// updates run -- two shared-memory round trips per half pass instead of two per cell.
-template <bool XFAST, bool DRIFT, bool V2>
+template <bool XFAST, bool DRIFT>
 __global__ void __launch_bounds__(512, 2) sor_rb_tiled_kernel(RbArgs A) {
 	extern __shared__ float smem_rb[];
 	float* s_f = smem_rb;
@@ -509,44 +498,6 @@ __global__ void __launch_bounds__(512, 2) sor_rb_tiled_kernel(RbArgs A) {
 			const int lx = lxa + 64 * half;
 			if (lx > hi) break;
 			int e = rb_index(lx, ly0), ex = rb_index(lx + 1, ly0);
-			if (V2) {
-				constexpr int R = (kRbW - 2) / 16 + 1;  // rows ly0, ly0+16, ... <= hi <= kRbW-2: at most 5
-				unsigned cd[R];
-				float vfc[R], vfp[R], vsc[R], vsp[R], pp[R], dr[R];
-#pragma unroll
-				for (int r = 0; r < R; r++) cd[r] = (ly0 + 16 * r <= hi) ? (unsigned)s_c[e + r * 16 * kRbRow] : 0u;
-#pragma unroll
-				for (int r = 0; r < R; r++) {
-					const int er = e + r * 16 * kRbRow, exr = ex + r * 16 * kRbRow;
-					vfc[r] = vfp[r] = vsc[r] = vsp[r] = pp[r] = dr[r] = 0.f;
-					if (cd[r] & 1u) {
-						vfc[r] = s_f[er]; vfp[r] = s_f[exr]; vsc[r] = s_s[er]; vsp[r] = s_s[er + kRbRow]; pp[r] = s_p[er];
-						if (DRIFT) dr[r] = s_d[er];
-					}
-				}
-#pragma unroll
-				for (int r = 0; r < R; r++) {
-					if (!(cd[r] & 1u)) continue;
-					const int er = e + r * 16 * kRbRow, exr = ex + r * 16 * kRbRow, eyr = er + kRbRow;
-					float div = XFAST ? ((vfp[r] - vfc[r]) + vsp[r]) - vsc[r] : ((vsp[r] - vsc[r]) + vfp[r]) - vfc[r];
-					if (DRIFT) div -= dr[r];
-					if (cd[r] == 31u) {
-						float pv = (-div * 0.25f) * A.omega;
-						s_p[er] = pp[r] + A.cp * pv;
-						s_f[er] = vfc[r] - pv; s_f[exr] = vfp[r] + pv; s_s[er] = vsc[r] - pv; s_s[eyr] = vsp[r] + pv;
-					} else {
-						const unsigned c = cd[r];
-						float sfm = (c & 2u) ? 1.f : 0.f, sfp = (c & 4u) ? 1.f : 0.f;
-						float ssm = (c & 8u) ? 1.f : 0.f, ssp = (c & 16u) ? 1.f : 0.f;
-						float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
-						float pv = -div / ssum;
-						pv *= A.omega;
-						s_p[er] = pp[r] + A.cp * pv;
-						s_f[er] = vfc[r] - sfm * pv; s_f[exr] = vfp[r] + sfp * pv;
-						s_s[er] = vsc[r] - ssm * pv; s_s[eyr] = vsp[r] + ssp * pv;
-					}
-				}
-			} else
 			for (int ly = ly0; ly <= hi; ly += 16, e += 16 * kRbRow, ex += 16 * kRbRow) {
 				const int ey = e + kRbRow;
 				const unsigned cd = s_c[e];
@@ -605,12 +556,10 @@ int sor_rb_round(SorWorkspace* w, const SorGrid& g, float* out_f, float* out_s, 
 	A.code = w->code; A.drift = use_drift ? w->drift : nullptr; A.row_lo = row_lo; A.row_hi = row_hi;
 	A.passes = std::min(passes, kRbK); A.colour0 = colour0 & 1; A.tiles_x = (g.nf + kRbT - 1) / kRbT; A.cp = cp; A.omega = omega;
 	const int tiles_y = (row_hi - row_lo + kRbT - 1) / kRbT;
-	static const bool v2 = getenv("FLIPGPU_RB_V2") && atoi(getenv("FLIPGPU_RB_V2")) != 0;  // opt-in until validated on hardware
-#define FG_RB_FN(V2V)                                                                                                                \
-	(g.x_fast ? (use_drift ? (const void*)sor_rb_tiled_kernel<true, true, V2V> : (const void*)sor_rb_tiled_kernel<true, false, V2V>) \
-	          : (use_drift ? (const void*)sor_rb_tiled_kernel<false, true, V2V> : (const void*)sor_rb_tiled_kernel<false, false, V2V>))
-	const void* fn = v2 ? FG_RB_FN(true) : FG_RB_FN(false);
-#undef FG_RB_FN
+	// (a variant that batched a thread's five cells per colour pass -- two shared-memory round trips per half pass -- measured
+	// 4.58 vs 4.06 ms per solve at S2 on B200 and was dropped: profiles/r2_ab_v2_variants_4096.jsonl)
+	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_rb_tiled_kernel<true, true> : (const void*)sor_rb_tiled_kernel<true, false>)
+	                          : (use_drift ? (const void*)sor_rb_tiled_kernel<false, true> : (const void*)sor_rb_tiled_kernel<false, false>);
 	const size_t smem = (size_t)kRbBox * ((use_drift ? 4 : 3) * sizeof(float) + 1);
 	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	void* args[] = {&A};
@@ -652,11 +601,15 @@ struct StripArgs {
 	int* counter;
 	float cp, omega;
 	unsigned long long* prof;  // [0] dependency wait [1] compute [2] everything else (cycles, thread 0), [4] strips
+	int* status;
 };
 
-__device__ __forceinline__ void wait_progress(const int* pr, int need) {
-	// bounded spin (~seconds): a scheduling bug must surface as a wrong answer in the tests, never as a hung GPU
-	for (long long spins = 0; *((volatile const int*)pr) < need && spins < (1ll << 26); spins++) __nanosleep(32);
+__device__ __forceinline__ void wait_progress(const int* pr, int need, int* status) {
+	// bounded spin (~seconds): a stall must never hang the GPU; a time-out raises the solver's error word, which the host
+	// reports as FLIPGPU_ESTATE at its next synchronising call
+	long long spins = 0;
+	for (; *((volatile const int*)pr) < need && spins < (1ll << 26); spins++) __nanosleep(32);
+	if (spins == (1ll << 26)) atomicExch(status, FLIPGPU_ESTATE);
 }
 
 template <bool XFAST, bool DRIFT>
@@ -690,8 +643,8 @@ __global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_strip_kernel(Stri
 		auto load_rows = [&](int lo, int hi) {   // rows [lo, hi) -> ring; rows outside the grid become inert (code 0)
 			if (tid == 0) {
 				int need = min(hi, ns);
-				if (dep_a) wait_progress(dep_a, need);
-				if (dep_b) wait_progress(dep_b, need);
+				if (dep_a) wait_progress(dep_a, need, A.status);
+				if (dep_b) wait_progress(dep_b, need, A.status);
 				__threadfence();
 			}
 			__syncthreads();
@@ -750,8 +703,8 @@ __global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_strip_kernel(Stri
 			if (tid == 0) {
 				long long w0 = clock64();
 				int need = min(pf_lo + kG, ns);
-				if (dep_a) wait_progress(dep_a, need);
-				if (dep_b) wait_progress(dep_b, need);
+				if (dep_a) wait_progress(dep_a, need, A.status);
+				if (dep_b) wait_progress(dep_b, need, A.status);
 				__threadfence();
 				c_wait += clock64() - w0;
 			}
@@ -849,7 +802,7 @@ int sor_solve_strips(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, 
 	StripArgs A;
 	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
 	A.drift = use_drift ? w->drift : nullptr; A.strips = w->strips; A.n_strips = w->n_strips; A.ni = w->ni;
-	A.kc = w->kc; A.iters = iters; A.progress = w->progress; A.counter = w->counter; A.cp = cp; A.omega = omega; A.prof = w->prof;
+	A.kc = w->kc; A.iters = iters; A.progress = w->progress; A.counter = w->counter; A.cp = cp; A.omega = omega; A.prof = w->prof; A.status = w->status;
 	const int warps = std::max(w->kc, (kG * kBoxW + kTile - 1) / kTile);  // >= 12 warps so one prefetch element per thread
 	dim3 block(kTile, warps);
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_strip_kernel<true, true> : (const void*)sor_gs_strip_kernel<true, false>)
@@ -862,6 +815,7 @@ int sor_solve_strips(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, 
 	int blocks = std::min(w->n_strips, std::max(1, per_sm) * w->sms);
 	void* args[] = {&A};
 	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, smem, st));
+	FG_CUDA(cudaMemcpyAsync(w->h_status, w->status, 4, cudaMemcpyDeviceToHost, st));
 	if (lc) lc->n += 2;
 	return FLIPGPU_OK;
 }

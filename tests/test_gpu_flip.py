@@ -190,16 +190,8 @@ def test_solver_blocked_wavefront_chunking(tank_states, iters):
             assert_bit_equal(sim.readback(name), getattr(oo, name), f"blocked wavefront {name} iters={iters} drift={drift}")
 
 
-def test_solver_blocked_equals_diagonal_on_a_large_grid():
-    """1024^2 dam-break, 6 whole steps: blocked and unblocked wavefront kernels give bit-identical trajectories
-    (many tiles per wave, all three inter-tile dependencies active, 4 chunks)."""
-    outs = []
-    for order in (sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL):
-        sim, kw, g = sg.scenes.make_flip_tank("synthetic", N=1024)
-        sim.simulate(**kw, n_steps=6, solver_order=order, update_colors=False)
-        outs.append((sim.readback("particle_pos"), sim.readback("u"), sim.readback("v"), sim.readback("p")))
-    for a, b in zip(*outs):
-        assert_bit_equal(a, b, "blocked vs diagonal")
+# (the large-grid solver check -- many tiles per wave, every inter-tile dependency, the obstacle -- is
+#  tests/test_gpu_bigscene.py::test_big_solver_lexicographic_bit_identical, against the CPU oracle at 1024^2)
 
 
 def test_non_binary_s_takes_the_general_kernel(tank_states):
