@@ -1,18 +1,34 @@
-"""Blocked-solver phase profile (FLIPGPU_SOR_PROFILE=1) on the dam-break (diagnostic, GPU box)."""
-import sys, os, ctypes as C
-os.environ["FLIPGPU_SOR_PROFILE"] = "1"
+"""Solver-only timing (diagnostic, GPU box): one pressure solve of the synthetic dam-break state after a few steps, per
+solver order, with a bit-comparison of the lexicographic variants against each other.
+usage: python scripts/solver_probe.py [N=4096] [iters=50] [with_obstacle=0]"""
+import sys, os, json, time
+import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 import simsandgames_b200 as sg
-N = int(sys.argv[1]); K = 5
-sim, kw, g = sg.scenes.make_flip_tank("synthetic", N=N)
-sim.simulate(**kw, n_steps=3, update_colors=False)
-sim.synchronize(); sim.enable_timings(True); sim.reset_timings()
-out0 = (C.c_ulonglong * 8)(); sim._lib.flip_debug_solver_profile(sim._h, out0)
-sim.simulate(**kw, n_steps=K, update_colors=False); sim.synchronize()
-out = (C.c_ulonglong * 8)(); sim._lib.flip_debug_solver_profile(sim._h, out)
-d = [out[i] - out0[i] for i in range(5)]
-tiles = d[4]
-print("solve ms/step", sim.timings()["solve"] / K, "tiles/solve", out[5], "Kc", out[6], "chunks", out[7])
-for name, v in zip(("dep wait", "compute", "other", "-"), d[:4]):
-    print(f"  {name:10s} {v / tiles:12.0f} cycles/strip  ({v / tiles / 1.9e3:.1f} us @1.9GHz)")
-print("  strips per solve", tiles / K)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+obst = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
+sim, kw, g = sg.scenes.make_flip_tank("synthetic", N=N, with_obstacle=obst)
+kw = dict(kw, num_pressure_iters=min(kw["num_pressure_iters"], 50))
+sim.simulate(**kw, n_steps=4, update_colors=False)
+sim.transferVelocitiesToGrid() if False else None
+u0, v0 = sim.readback("u").copy(), sim.readback("v").copy()
+stream = torch.cuda.ExternalStream(sim.stream)
+res = {}
+for name, order in (("systolic", sg.LEX_WAVEFRONT), ("tiled", sg.LEX_TILED), ("red_black", sg.RED_BLACK)):
+    ms = []
+    for rep in range(4):
+        sim.upload("u", u0); sim.upload("v", v0)
+        sim.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.solveIncompressibility(iters, kw["dt"], 1.9, True, solver_order=order)
+        e1.record(stream)
+        sim.synchronize(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    res[name] = (min(ms[1:]), sim.readback("u").copy(), sim.readback("v").copy(), sim.readback("p").copy())
+same = all(np.array_equal(res["systolic"][i].view(np.int32), res["tiled"][i].view(np.int32)) for i in (1, 2, 3))
+print(json.dumps({"N": N, "iters": iters, "obstacle": obst, "ms": {k: round(v[0], 3) for k, v in res.items()},
+                  "systolic_equals_tiled_bitwise": bool(same), "env": {k: v for k, v in os.environ.items() if k.startswith("FLIPGPU_")}}), flush=True)
+sim.close()

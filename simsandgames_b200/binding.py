@@ -18,7 +18,7 @@ _LIB = None
 LEX_WAVEFRONT = 0   # FlipSolverOrder of include/flipgpu.h: 0 = the reference order
 RED_BLACK = 1
 LEX_DIAGONAL = 2
-LEX_STRIPS = 3
+LEX_TILED = 3
 
 FLIP_FIELDS = {  # name -> (enum value, numpy dtype)   order == FlipField in flipgpu.h
     "u": (0, np.float32), "v": (1, np.float32), "du": (2, np.float32), "dv": (3, np.float32),

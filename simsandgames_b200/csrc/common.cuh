@@ -83,10 +83,14 @@ int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]);
 int sor_workspace_check(SorWorkspace* w);  // after a stream sync: FLIPGPU_ESTATE if a solver dependency wait timed out
 int sor_solve_tiled(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
                     LaunchCounter* lc);
-int sor_solve_strips(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
-                     LaunchCounter* lc);
+struct SysWorkspace;  // register-systolic wavefront kernel (sor_systolic.cu)
+void sys_workspace_free(SysWorkspace* w);
+int sys_workspace_check(SysWorkspace* w);
+SysWorkspace** sor_workspace_sys(SorWorkspace** ws);
+int sor_solve_systolic(SysWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
+                       LaunchCounter* lc);
 // order: FlipSolverOrder.  s_binary: every s is 0 or 1 (required by the blocked kernel's 1-byte cell code;
-// otherwise LEX_WAVEFRONT falls back to the unblocked diagonal kernel, same results).
+// otherwise the lexicographic orders fall back to the unblocked diagonal kernel, same results).
 int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, int order, bool s_binary,
               cudaStream_t st, LaunchCounter* lc, bool* swapped = nullptr);
 // temporally blocked red-black (sor_tiled.cu): cell constants once per solve, then rounds of up to 8 colour passes

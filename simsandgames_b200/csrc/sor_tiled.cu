@@ -1,4 +1,5 @@
-// Blocked-wavefront Gauss-Seidel SOR: the reference's lexicographic sweep order
+// Blocked-wavefront Gauss-Seidel SOR in shared memory (FLIP_SOLVER_LEX_TILED; the default lexicographic solver is the
+// register-systolic kernel of sor_systolic.cu, this one is kept as an independent cross-check): the reference's lexicographic sweep order
 // (flip_fluid.h:458-494 / fluid.h:106-138), bit for bit, staged through shared memory with
 // temporal blocking, as ONE persistent kernel per solve.
 //
@@ -276,9 +277,7 @@ struct SorWorkspace {
 	unsigned char* act = nullptr;  // activity of the unskewed TxT squares
 	int na = 0, nb = 0;
 	unsigned long long* prof = nullptr;
-	int2* strips = nullptr;   // (I, q) in wave order I + 2q (streaming-strip kernel)
-	int* progress = nullptr;  // per strip: rows S < progress are final in global memory
-	int n_strips = 0;
+	SysWorkspace* sys = nullptr;  // workspace of the register-systolic kernel (sor_systolic.cu), the default lexicographic solver
 	int sms = 0;
 	int* status = nullptr;    // device error word raised by a dependency wait that timed out ...
 	int* h_status = nullptr;  // ... mirrored into pinned host memory behind every solve launch
@@ -295,15 +294,21 @@ int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]) {
 
 void sor_workspace_free(SorWorkspace* w) {
 	if (!w) return;
-	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter); cudaFree(w->prof); cudaFree(w->strips); cudaFree(w->progress); cudaFree(w->act);
+	cudaFree(w->code); cudaFree(w->drift); cudaFree(w->tiles); cudaFree(w->flags); cudaFree(w->counter); cudaFree(w->prof); cudaFree(w->act);
 	cudaFree(w->status);
 	if (w->h_status) cudaFreeHost(w->h_status);
+	sys_workspace_free(w->sys);
 	delete w;
+}
+SysWorkspace** sor_workspace_sys(SorWorkspace** wsp) {
+	if (!*wsp) *wsp = new SorWorkspace;
+	return &(*wsp)->sys;
 }
 
 // Call after the stream that ran the solves has been synchronised: FLIPGPU_ESTATE if an inter-CTA dependency wait of a
 // persistent solver kernel timed out (the pressure field of that solve is then incomplete).
 int sor_workspace_check(SorWorkspace* w) {
+	if (w && w->sys) FG_TRY(sys_workspace_check(w->sys));
 	if (!w || !w->h_status || *w->h_status == 0) return FLIPGPU_OK;
 	fg::set_error("pressure solve: an inter-CTA dependency wait timed out (GPU preempted or oversubscribed?); the solve is incomplete");
 	return FLIPGPU_ESTATE;
@@ -363,20 +368,6 @@ static int plan(SorWorkspace* w, const SorGrid& g, int iters, cudaStream_t st) {
 		FG_CUDA(cudaMemcpyAsync(w->tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
 		FG_CUDA(cudaMemsetAsync(w->flags, 0, (size_t)ni * nj * nq * 4, st));
 		FG_CUDA(cudaStreamSynchronize(st));  // tiles is a host temporary
-		std::vector<int2> strips;
-		for (int wv = 0; wv <= (ni - 1) + 2 * (nq - 1); wv++)
-			for (int q = 0; q < nq; q++) {
-				int I = wv - 2 * q;
-				if (I < 0) break;
-				if (I < ni) strips.push_back(make_int2(I, q));
-			}
-		cudaFree(w->strips); cudaFree(w->progress);
-		w->strips = nullptr; w->progress = nullptr;
-		FG_CUDA(cudaMalloc(&w->strips, strips.size() * sizeof(int2)));
-		FG_CUDA(cudaMalloc(&w->progress, (size_t)ni * nq * 4));
-		FG_CUDA(cudaMemcpyAsync(w->strips, strips.data(), strips.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-		FG_CUDA(cudaStreamSynchronize(st));
-		w->n_strips = (int)strips.size();
 		w->iters = iters; w->kc = kc; w->ni = ni; w->nj = nj; w->nq = nq; w->n_tiles = (int)tiles.size();
 		w->epoch = 0;
 	}
@@ -574,249 +565,6 @@ int sor_rb_deactivate_rows(SorWorkspace* w, const SorGrid& g, int row_lo, int ro
 	row_lo = std::max(row_lo, 0); row_hi = std::min(row_hi, g.ns);
 	if (!w || !w->code || row_hi <= row_lo) return FLIPGPU_OK;
 	FG_CUDA(cudaMemsetAsync(w->code + (size_t)g.nf * row_lo, 0, (size_t)g.nf * (row_hi - row_lo), st));
-	return FLIPGPU_OK;
-}
-
-// ===================================================================================================
-// Streaming-strip variant of the blocked wavefront (same order, same bits; the default).
-// A CTA owns one skewed tile COLUMN (I, q) and marches down all rows: lane a works on skewed row b = t - a at
-// step t, so after a 31-step ramp every lane is busy every step (the square tiles above idle half the lanes)
-// and consecutive strips overlap as a pipeline: strip I trails strip I-1 by ~T+Kc+2G rows instead of waiting
-// for whole tiles.  Rows stream through a ring buffer in shared memory: every G steps the CTA loads the next
-// G rows (after the producer strips -- (I-1,q) and (I+1,q-1) -- have published them) and writes back the G rows
-// that can no longer change, then publishes its own progress counter.
-constexpr int kRing = 96;  // ring rows: live window T+Kc+2 plus one block ahead and one behind
-constexpr int kG = 8;      // steps per load/write-back block (kG*kBoxW = 384 prefetch elements <= threads per CTA)
-
-struct StripArgs {
-	int nf, ns;
-	float* vel_f;
-	float* vel_s;
-	float* p;
-	const unsigned char* code;
-	const float* drift;
-	const int2* strips;
-	int n_strips, ni, kc, iters;
-	int* progress;
-	int* counter;
-	float cp, omega;
-	unsigned long long* prof;  // [0] dependency wait [1] compute [2] everything else (cycles, thread 0), [4] strips
-	int* status;
-};
-
-__device__ __forceinline__ void wait_progress(const int* pr, int need, int* status) {
-	// bounded spin (~seconds): a stall must never hang the GPU; a time-out raises the solver's error word, which the host
-	// reports as FLIPGPU_ESTATE at its next synchronising call
-	long long spins = 0;
-	for (; *((volatile const int*)pr) < need && spins < (1ll << 26); spins++) __nanosleep(32);
-	if (spins == (1ll << 26)) atomicExch(status, FLIPGPU_ESTATE);
-}
-
-template <bool XFAST, bool DRIFT>
-__global__ void __launch_bounds__(kTile * kMaxChunk, 2) sor_gs_strip_kernel(StripArgs A) {
-	extern __shared__ float smem_f[];
-	float* s_vf = smem_f;
-	float* s_vs = s_vf + kRing * kBoxW;
-	float* s_p = s_vs + kRing * kBoxW;
-	float* s_dr = s_p + kRing * kBoxW;  // only touched when DRIFT
-	unsigned char* s_code = reinterpret_cast<unsigned char*>(s_dr + (DRIFT ? kRing * kBoxW : 0));
-	__shared__ int s_strip;
-	const int tid = threadIdx.y * kTile + threadIdx.x;
-	const int nthreads = kTile * blockDim.y;
-	const int nf = A.nf, ns = A.ns;
-	for (;;) {
-		__syncthreads();
-		if (tid == 0) s_strip = atomicAdd(A.counter, 1);
-		__syncthreads();
-		const int si = s_strip;
-		if (si >= A.n_strips) return;
-		const int2 sq = A.strips[si];
-		const int I = sq.x, q = sq.y;
-		const int kq = min(A.kc, A.iters - q * A.kc);
-		const int F0 = 1 + I * kTile, FB = F0 - A.kc + 1;
-		const int* dep_a = I > 0 ? A.progress + q * A.ni + I - 1 : nullptr;
-		const int* dep_b = q > 0 ? A.progress + (q - 1) * A.ni + min(I + 1, A.ni - 1) : nullptr;
-		int* my_progress = A.progress + q * A.ni + I;
-		const int nb = (ns - 2) + (kq - 1);      // skewed rows b = S - 1 + k
-		const int n_steps = nb + kTile - 1;
-
-		auto load_rows = [&](int lo, int hi) {   // rows [lo, hi) -> ring; rows outside the grid become inert (code 0)
-			if (tid == 0) {
-				int need = min(hi, ns);
-				if (dep_a) wait_progress(dep_a, need, A.status);
-				if (dep_b) wait_progress(dep_b, need, A.status);
-				__threadfence();
-			}
-			__syncthreads();
-			for (int e = tid; e < (hi - lo) * kBoxW; e += nthreads) {
-				int lf = e % kBoxW, S = lo + e / kBoxW;
-				int F = FB + lf;
-				float vf = 0.f, vs = 0.f, pp = 0.f, dr = 0.f;
-				unsigned char cd = 0;
-				if (F >= 0 && F < nf && S >= 0 && S < ns) {
-					size_t c = (size_t)F + (size_t)nf * S;
-					vf = __ldcg(A.vel_f + c); vs = __ldcg(A.vel_s + c); pp = __ldcg(A.p + c);
-					cd = A.code[c];
-					if (DRIFT) dr = A.drift[c];
-				}
-				int idx = (S % kRing) * kBoxW + lf;
-				s_vf[idx] = vf; s_vs[idx] = vs; s_p[idx] = pp; s_code[idx] = cd;
-				if (DRIFT) s_dr[idx] = dr;
-			}
-		};
-		// columns this strip owns in every row: cells F0-kq+1 .. F0+T-1, plus the high-side face column F0+T
-		const int own_lo = max(F0 - kq + 1, 1), own_hi = min(F0 + kTile - 1, nf - 2);
-		auto write_rows = [&](int lo, int hi) {  // rows [lo, hi) clipped to the rows that hold solver state
-			lo = max(lo, 1); hi = min(hi, ns);
-			for (int e = tid; e < (hi - lo) * kBoxW; e += nthreads) {
-				int lf = e % kBoxW, S = lo + e / kBoxW;
-				int F = FB + lf;
-				if (F < own_lo || F > own_hi + 1) continue;
-				int idx = (S % kRing) * kBoxW + lf;
-				size_t c = (size_t)F + (size_t)nf * S;
-				if (S <= ns - 2) {
-					__stcg(A.vel_f + c, s_vf[idx]);                   // own cells' low faces + the face right of the last own cell
-					if (F <= own_hi) __stcg(A.p + c, s_p[idx]);
-				}
-				if (F <= own_hi) __stcg(A.vel_s + c, s_vs[idx]);       // rows 1..ns-1: row ns-1 is the top face of row ns-2
-			}
-		};
-
-		// Software pipeline, one block = kG steps:  the rows of block n+2 are fetched into registers while block n
-		// computes (L2 latency hidden), stored into the ring afterwards; the rows that went final during block n-1
-		// were issued to global memory at the end of block n-1 and are fenced + published at the end of block n
-		// (so the fence finds them long complete).
-		load_rows(0, 2 * kG + 2);   // blocks 0 and 1 need rows <= 2kG+1
-		__syncthreads();
-		int written_hi = 0, published = 0;
-		const int a = threadIdx.x;
-		long long c_wait = 0, c_comp = 0, c_begin = clock64();
-		// active steps of this thread: b = t-a in [0,nb) and S = 1+b-k in [1, ns-2]
-		const int kk = threadIdx.y;
-		const int t_lo = kk < kq ? a + kk : 0x7fffffff, t_hi = kk < kq ? a + min(nb, ns - 2 + kk) : 0;
-		int e = (1 % kRing) * kBoxW + (a - kk + A.kc - 1);   // row S = 1 at t = t_lo
-		int eu = (2 % kRing) * kBoxW + (a - kk + A.kc - 1);
-		const int pf_lf = tid % kBoxW, pf_row = tid / kBoxW;   // this thread's element of a prefetched block (tid < kG*kBoxW)
-		for (int t0 = 0; t0 < n_steps; t0 += kG) {
-			// ---- issue the prefetch of rows [t0+2kG+2, t0+3kG+2)
-			const int pf_lo = t0 + 2 * kG + 2;
-			if (tid == 0) {
-				long long w0 = clock64();
-				int need = min(pf_lo + kG, ns);
-				if (dep_a) wait_progress(dep_a, need, A.status);
-				if (dep_b) wait_progress(dep_b, need, A.status);
-				__threadfence();
-				c_wait += clock64() - w0;
-			}
-			__syncthreads();
-			float pf_vf = 0.f, pf_vs = 0.f, pf_p = 0.f, pf_dr = 0.f;
-			unsigned char pf_cd = 0;
-			const int pf_S = pf_lo + pf_row, pf_F = FB + pf_lf;
-			const bool pf_on = tid < kG * kBoxW;
-			if (pf_on && pf_F >= 0 && pf_F < nf && pf_S < ns) {
-				size_t c = (size_t)pf_F + (size_t)nf * pf_S;
-				pf_vf = __ldcg(A.vel_f + c); pf_vs = __ldcg(A.vel_s + c); pf_p = __ldcg(A.p + c);
-				pf_cd = A.code[c];
-				if (DRIFT) pf_dr = A.drift[c];
-			}
-			// ---- compute kG steps.  Thread (a, k) owns skewed column a of iteration k: its cell row S = 1+t-a-k grows
-			// by one per step, so the ring offsets advance incrementally (no modulo in the loop).
-			long long k0 = clock64();
-			const int t1 = min(t0 + kG, n_steps);
-			for (int t = t0; t < t1; t++) {
-				if (t >= t_lo && t < t_hi) {
-					unsigned cd = s_code[e];
-					if (cd & 1u) {
-						float vfc = s_vf[e], vfp = s_vf[e + 1], vsc = s_vs[e], vsp = s_vs[eu];
-						float div = XFAST ? ((vfp - vfc) + vsp) - vsc : ((vsp - vsc) + vfp) - vfc;
-						if (DRIFT) div -= s_dr[e];   // the stored term is max(0, density-rest): subtracting 0 is exact
-						float pv;
-						if (cd == 31u) {             // all four neighbours open: s_sum = 4, x/4 == x*0.25 exactly
-							pv = (-div * 0.25f) * A.omega;
-							s_p[e] += A.cp * pv;
-							s_vf[e] = vfc - pv; s_vf[e + 1] = vfp + pv; s_vs[e] = vsc - pv; s_vs[eu] = vsp + pv;
-						} else {
-							float sfm = (cd & 2u) ? 1.f : 0.f, sfp = (cd & 4u) ? 1.f : 0.f;
-							float ssm = (cd & 8u) ? 1.f : 0.f, ssp = (cd & 16u) ? 1.f : 0.f;
-							float ssum = XFAST ? ((sfm + sfp) + ssm) + ssp : ((ssm + ssp) + sfm) + sfp;
-							pv = -div / ssum;
-							pv *= A.omega;
-							s_p[e] += A.cp * pv;
-							s_vf[e] = vfc - sfm * pv; s_vf[e + 1] = vfp + sfp * pv;
-							s_vs[e] = vsc - ssm * pv; s_vs[eu] = vsp + ssp * pv;
-						}
-					}
-					e = eu;
-					eu += kBoxW;
-					if (eu >= kRing * kBoxW) eu -= kRing * kBoxW;
-				}
-				__syncthreads();
-			}
-			c_comp += clock64() - k0;
-			// ---- land the prefetched rows in the ring (their slots held rows written back >= 2 blocks ago)
-			if (pf_on) {
-				int idx = (pf_S % kRing) * kBoxW + pf_lf;
-				s_vf[idx] = pf_vf; s_vs[idx] = pf_vs; s_p[idx] = pf_p; s_code[idx] = pf_cd;
-				if (DRIFT) s_dr[idx] = pf_dr;
-			}
-			// ---- write back the rows that went final during this block and publish them.
-			// rows <= (t1-1) - 31 - kc can no longer change (lane 31, last iteration of the chunk is past them).
-			// Release pattern: every thread stores, bar.sync, then ONE thread fences (cumulative at gpu scope) and
-			// writes the progress word -- the other warps go straight on to the next block.
-			int hi = t1 - kTile - A.kc;
-			if (hi > written_hi) {
-				write_rows(written_hi, hi);
-				written_hi = hi;
-			}
-			__syncthreads();
-			if (tid == 0 && written_hi > published) {
-				__threadfence();
-				*((volatile int*)my_progress) = written_hi;
-			}
-			published = written_hi;
-		}
-		write_rows(written_hi, ns);
-		__syncthreads();
-		if (tid == 0) {
-			__threadfence();
-			*((volatile int*)my_progress) = 0x7fffffff;
-			if (A.prof) {
-				long long tot = clock64() - c_begin;
-				atomicAdd(A.prof + 0, (unsigned long long)c_wait); atomicAdd(A.prof + 1, (unsigned long long)c_comp);
-				atomicAdd(A.prof + 2, (unsigned long long)(tot - c_wait - c_comp)); atomicAdd(A.prof + 4, 1ull);
-			}
-		}
-	}
-}
-
-int sor_solve_strips(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
-                     LaunchCounter* lc) {
-	if (iters <= 0 || g.nf < 3 || g.ns < 3) return FLIPGPU_OK;
-	if (!*wsp) *wsp = new SorWorkspace;
-	SorWorkspace* w = *wsp;
-	FG_TRY(plan(w, g, iters, st));
-	bool use_drift = drift && g.density && g.rest;
-	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, nullptr, 0, 0, (size_t)g.nf * g.ns);
-	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
-	FG_CUDA(cudaMemsetAsync(w->progress, 0, (size_t)w->ni * w->nq * 4, st));
-	StripArgs A;
-	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
-	A.drift = use_drift ? w->drift : nullptr; A.strips = w->strips; A.n_strips = w->n_strips; A.ni = w->ni;
-	A.kc = w->kc; A.iters = iters; A.progress = w->progress; A.counter = w->counter; A.cp = cp; A.omega = omega; A.prof = w->prof; A.status = w->status;
-	const int warps = std::max(w->kc, (kG * kBoxW + kTile - 1) / kTile);  // >= 12 warps so one prefetch element per thread
-	dim3 block(kTile, warps);
-	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_gs_strip_kernel<true, true> : (const void*)sor_gs_strip_kernel<true, false>)
-	                          : (use_drift ? (const void*)sor_gs_strip_kernel<false, true> : (const void*)sor_gs_strip_kernel<false, false>);
-	size_t smem = (size_t)kRing * kBoxW * ((use_drift ? 4 : 3) * sizeof(float) + 1);
-	FG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	int per_sm = 0;
-	FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTile * warps, smem));
-	if (const char* e = getenv("FLIPGPU_STRIP_CTAS")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
-	int blocks = std::min(w->n_strips, std::max(1, per_sm) * w->sms);
-	void* args[] = {&A};
-	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, smem, st));
-	FG_CUDA(cudaMemcpyAsync(w->h_status, w->status, 4, cudaMemcpyDeviceToHost, st));
-	if (lc) lc->n += 2;
 	return FLIPGPU_OK;
 }
 
