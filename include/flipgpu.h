@@ -71,15 +71,16 @@ typedef enum {
 } FlipField;
 
 typedef enum {
-	FLIP_SOLVER_LEX_WAVEFRONT = 0, /* the reference's lexicographic loop order (flip_fluid.h:458-494) as an anti-diagonal
-	                                  wavefront pipelined through registers (one warp per 32-column strip, the iterations
-	                                  of a chunk as pipeline stages): bit-identical u,v,p.  Value 0: a zero-initialised
-	                                  FlipStepParams runs the reference's own order */
+	FLIP_SOLVER_LEX_WAVEFRONT = 0, /* the reference's lexicographic loop order (flip_fluid.h:458-494) as a blocked anti-diagonal
+	                                  wavefront: skewed square tiles with temporal blocking in shared memory; bit-identical
+	                                  u,v,p.  Value 0: a zero-initialised FlipStepParams runs the reference's own order */
 	FLIP_SOLVER_RED_BLACK = 1,     /* red-black order (north_star's named order); bounded against the reference order (T2).
 	                                  At the reference's 50 sweeps it is less stable than the reference order on tall
 	                                  liquid columns (profiles/r1_stability.md) */
 	FLIP_SOLVER_LEX_DIAGONAL = 2,  /* same order, unblocked one-diagonal-per-grid-sync kernel (cross-check / non-binary s) */
-	FLIP_SOLVER_LEX_TILED = 3      /* same order, skewed square tiles with temporal blocking in shared memory (the r1 kernel; cross-check) */
+	FLIP_SOLVER_LEX_SYSTOLIC = 3   /* same order, register-systolic pipeline (one warp per 32-column strip, the iterations of a
+	                                  chunk as pipeline stages, no block-wide barrier; sor_systolic.cu): bit-identical, slower
+	                                  than the tiled kernel on B200 so far (profiles/r2_systolic.md) */
 } FlipSolverOrder;
 
 /* the 13 arguments of FlipFluid::simulate (flip_fluid.h:560-565) + two switches */

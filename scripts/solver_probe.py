@@ -16,7 +16,8 @@ sim.transferVelocitiesToGrid() if False else None
 u0, v0 = sim.readback("u").copy(), sim.readback("v").copy()
 stream = torch.cuda.ExternalStream(sim.stream)
 res = {}
-for name, order in (("systolic", sg.LEX_WAVEFRONT), ("tiled", sg.LEX_TILED), ("red_black", sg.RED_BLACK)):
+VARIANTS = (("systolic", sg.LEX_SYSTOLIC), ("tiled", sg.LEX_WAVEFRONT)) if os.environ.get("PROBE_LEX_ONLY") else (("systolic", sg.LEX_SYSTOLIC), ("tiled", sg.LEX_WAVEFRONT), ("red_black", sg.RED_BLACK))
+for name, order in VARIANTS:
     ms = []
     for rep in range(4):
         sim.upload("u", u0); sim.upload("v", v0)
@@ -28,6 +29,11 @@ for name, order in (("systolic", sg.LEX_WAVEFRONT), ("tiled", sg.LEX_TILED), ("r
         sim.synchronize(); torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     res[name] = (min(ms[1:]), sim.readback("u").copy(), sim.readback("v").copy(), sim.readback("p").copy())
+    if name == "systolic" and os.environ.get("FLIPGPU_SOR_PROFILE"):
+        pr = sim.solver_profile()
+        tasks = max(pr[4], 1)
+        print(json.dumps({"systolic_profile_cycles_per_task": {"wait": pr[0] / tasks, "flush": pr[1] / tasks, "land_fetch": pr[2] / tasks, "steps": pr[3] / tasks,
+                                                              "total": pr[5] / tasks}, "tasks": pr[4]}), flush=True)
 same = all(np.array_equal(res["systolic"][i].view(np.int32), res["tiled"][i].view(np.int32)) for i in (1, 2, 3))
 print(json.dumps({"N": N, "iters": iters, "obstacle": obst, "ms": {k: round(v[0], 3) for k, v in res.items()},
                   "systolic_equals_tiled_bitwise": bool(same), "env": {k: v for k, v in os.environ.items() if k.startswith("FLIPGPU_")}}), flush=True)

@@ -7,8 +7,8 @@ importing works anywhere, creating a simulation without the built library or wit
 device raises.
 """
 from .binding import (FlipFluidGPU, FluidGPU, FlipGpuError, lib_path, load_library, build_library,
-                      ShardedProjection, FlipFluidSharded, nccl_unique_id, slab_rows, FLIP_FIELDS, EULER_FIELDS, RED_BLACK, LEX_WAVEFRONT, LEX_DIAGONAL, LEX_TILED)
+                      ShardedProjection, FlipFluidSharded, nccl_unique_id, slab_rows, FLIP_FIELDS, EULER_FIELDS, RED_BLACK, LEX_WAVEFRONT, LEX_DIAGONAL, LEX_SYSTOLIC)
 from . import scenes
 
 __all__ = ["FlipFluidGPU", "FluidGPU", "FlipGpuError", "lib_path", "load_library", "build_library", "ShardedProjection", "FlipFluidSharded", "nccl_unique_id", "slab_rows",
-           "FLIP_FIELDS", "EULER_FIELDS", "RED_BLACK", "LEX_WAVEFRONT", "LEX_DIAGONAL", "LEX_TILED", "scenes"]
+           "FLIP_FIELDS", "EULER_FIELDS", "RED_BLACK", "LEX_WAVEFRONT", "LEX_DIAGONAL", "LEX_SYSTOLIC", "scenes"]

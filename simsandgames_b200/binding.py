@@ -18,7 +18,7 @@ _LIB = None
 LEX_WAVEFRONT = 0   # FlipSolverOrder of include/flipgpu.h: 0 = the reference order
 RED_BLACK = 1
 LEX_DIAGONAL = 2
-LEX_TILED = 3
+LEX_SYSTOLIC = 3
 
 FLIP_FIELDS = {  # name -> (enum value, numpy dtype)   order == FlipField in flipgpu.h
     "u": (0, np.float32), "v": (1, np.float32), "du": (2, np.float32), "dv": (3, np.float32),
@@ -65,7 +65,8 @@ class _EulerDims(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libflipgpu.so")
+    # FLIPGPU_LIB: an alternative build of the same library (A/B of compile-time variants, scripts/ only)
+    return os.environ.get("FLIPGPU_LIB") or os.path.join(_HERE, "libflipgpu.so")
 
 
 def build_library(verbose=False):
@@ -267,6 +268,12 @@ class FlipFluidGPU:
         n = C.c_longlong()
         _check(self._lib.flip_get_launch_count(self._h, C.byref(n)), "flip_get_launch_count")
         return n.value
+
+    def solver_profile(self):
+        """FLIPGPU_SOR_PROFILE=1: SM cycles the lexicographic solver spent per phase since the last call (8 counters)"""
+        out = (C.c_ulonglong * 8)()
+        _check(self._lib.flip_debug_solver_profile(self._h, out), "flip_debug_solver_profile")
+        return list(out)
 
     def close(self):
         if self._h:

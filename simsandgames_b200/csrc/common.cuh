@@ -86,6 +86,7 @@ int sor_solve_tiled(SorWorkspace** ws, const SorGrid& g, int iters, float cp, fl
 struct SysWorkspace;  // register-systolic wavefront kernel (sor_systolic.cu)
 void sys_workspace_free(SysWorkspace* w);
 int sys_workspace_check(SysWorkspace* w);
+int sys_workspace_profile(SysWorkspace* w, unsigned long long out[8]);
 SysWorkspace** sor_workspace_sys(SorWorkspace** ws);
 int sor_solve_systolic(SysWorkspace** ws, const SorGrid& g, int iters, float cp, float omega, bool drift, cudaStream_t st,
                        LaunchCounter* lc);

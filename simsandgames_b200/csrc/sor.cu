@@ -92,9 +92,9 @@ int sor_solve(SorWorkspace** ws, const SorGrid& g, int iters, float cp, float om
 	if (swapped) *swapped = false;
 	if (iters <= 0 || g.nf < 3 || g.ns < 3) return FLIPGPU_OK;
 	bool use_drift = drift && g.density && g.rest;
-	if (order == FLIP_SOLVER_LEX_WAVEFRONT && s_binary && ws) return sor_solve_systolic(sor_workspace_sys(ws), g, iters, cp, omega, drift, st, lc);
-	if (order == FLIP_SOLVER_LEX_TILED && s_binary && ws) return sor_solve_tiled(ws, g, iters, cp, omega, drift, st, lc);
-	if (order == FLIP_SOLVER_LEX_WAVEFRONT || order == FLIP_SOLVER_LEX_DIAGONAL || order == FLIP_SOLVER_LEX_TILED) {
+	if (order == FLIP_SOLVER_LEX_WAVEFRONT && s_binary && ws) return sor_solve_tiled(ws, g, iters, cp, omega, drift, st, lc);
+	if (order == FLIP_SOLVER_LEX_SYSTOLIC && s_binary && ws) return sor_solve_systolic(sor_workspace_sys(ws), g, iters, cp, omega, drift, st, lc);
+	if (order == FLIP_SOLVER_LEX_WAVEFRONT || order == FLIP_SOLVER_LEX_DIAGONAL || order == FLIP_SOLVER_LEX_SYSTOLIC) {
 		int dev = 0, sms = 0, per_sm = 0;
 		FG_CUDA(cudaGetDevice(&dev));
 		FG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

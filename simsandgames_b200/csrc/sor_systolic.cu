@@ -32,7 +32,12 @@ constexpr int kSysG = 4;                 // steps per phase (flush / publish / d
 constexpr int kSysWarps = 4;             // warps per CTA, one CTA per SM: one warp per scheduler
 constexpr int kSysRin = 32 + kSysG;      // rows of the skew rings (stage 0 in, stage K-1 out): window [t0-31, t0+G]
 constexpr int kSysRio = 16;              // rows of the strip-to-strip rings in shared memory (needs 2G+K-2 <= 16)
+constexpr int kSysPubEvery = 2;          // progress is published every this many phases
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef SYS_STEP_UNROLL
+#define SYS_STEP_UNROLL 1   // steps of a phase unrolled in the instruction stream (the two step bodies of K stages are large)
+#endif
+constexpr int kSysStepUnroll = SYS_STEP_UNROLL;
 
 // cell word: bit0 active | bits1-4 s != 0 at fast-, fast+, slow-, slow+ | bit5 s_sum==3 | bit6 s_sum==2 | bit7 s_sum==1 |
 // bit8 "general": active with a closed neighbour (the fast step body handles words 0 and 31 only)
@@ -72,13 +77,14 @@ struct SysArgs {
 	int* status;
 	float* ring;         // [nw][2][ns][RSF]
 	float cp, omega;
+	unsigned long long* prof;  // optional (FLIPGPU_SOR_PROFILE): cycles in [0] dependency waits [1] flush+publish [2] land+fetch [3] steps, [4] tasks, [5] task cycles
 };
 
 template <int K>
 struct SysLayout {
 	static constexpr int RSF = ((4 * (K - 1) + K) + 3) / 4 * 4;   // floats per ring row: (K-1) float4 hand-overs, then K column faces
 	static constexpr int kVfOff = 4 * (K - 1);
-	static constexpr int kWarpFloats = kSysRin * 32 * 5 + kSysRin * 32 * 3 + 2 * kSysRio * RSF;
+	static constexpr int kWarpFloats = kSysRin * 32 * 5 + kSysRin * 32 * 3 + 2 * kSysRio * RSF + 32 * 4;   // skew rings in, out, strip rings, scratch
 	static_assert(2 * kSysG + K - 2 <= kSysRio, "strip-to-strip ring too small");
 };
 
@@ -98,6 +104,25 @@ __device__ __forceinline__ float div3_rn(float x) {
 	return r == 0.f ? q0 : q1;   // keeps the sign of a zero quotient
 }
 
+// this lane's roles at the wrap of the strip and the ring addresses they use in the current step
+struct SysXchg {             // (shared-memory addresses, 32-bit)
+	int k31, k0;             // stage for which the lane is the last / the first column of the strip (>= K: none)
+	unsigned out_vf;         // io_out row (t-31-k31): column face of stage k31 ...
+	unsigned out_hand;       // ... and its float4 hand-over
+	unsigned in_hand;        // io_in row (t+1-k31), float4 hand-over of stage k31
+	unsigned in_vf;          // io_in row (t+1-k0), column face of stage k0
+	unsigned scratch;        // this lane's private float4
+};
+
+// single predicated shared-memory accesses (ptxas keeps these predicated)
+__device__ __forceinline__ void sts_if(bool p, unsigned addr, float v) {
+	asm volatile("{ .reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f32 [%1], %2; }" ::"r"((int)p), "r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_if(bool p, unsigned addr, float keep) {
+	asm volatile("{ .reg .pred q; setp.ne.s32 q, %1, 0; @q ld.shared.f32 %0, [%2]; }" : "+f"(keep) : "r"((int)p), "r"(addr) : "memory");
+	return keep;
+}
+
 // One step of a task: every lane advances its K stages by one row.
 //   compute block : straight-line, branch-free (the update is computed for every lane and committed under the cell's
 //                   "active" bit), so the K dependency chains of a lane interleave in ONE basic block;
@@ -106,13 +131,10 @@ __device__ __forceinline__ float div3_rn(float x) {
 //                   hand-over with the strip-to-strip rings in shared memory -- short divergent branches, kept out of the
 //                   compute block on purpose.
 template <int K, bool XFAST, bool DRIFT, bool GEN>
-__device__ __forceinline__ void sys_step(SysState<K, DRIFT>& s, const int t, const int lane, const int lane_hi, const int lane_lo,
-                                         const float* __restrict__ in_vf, const float* __restrict__ in_vs, const float* __restrict__ in_p,
-                                         const float2* __restrict__ in_cd, float* __restrict__ o_p, float* __restrict__ o_vs,
-                                         float* __restrict__ o_vf, const float* __restrict__ io_in, float* __restrict__ io_out,
-                                         const int s0, const int s1, const int sf, const float cp, const float omega) {
-	using L = SysLayout<K>;
-	float vfh_out[K];
+__device__ __forceinline__ void sys_compute(SysState<K, DRIFT>& s, float (&vfh_out)[K], const int lane, const int lane_hi,
+                                            const float* __restrict__ in_vf, const float* __restrict__ in_vs, const float* __restrict__ in_p,
+                                            const float2* __restrict__ in_cd, float* __restrict__ o_p, float* __restrict__ o_vs,
+                                            float* __restrict__ o_vf, const int s0, const int s1, const int sf, const float cp, const float omega) {
 #pragma unroll
 	for (int kk = 0; kk < K; kk++) {
 		const int k = K - 1 - kk;                       // high stages first: stage k consumes what stage k-1 left LAST step
@@ -161,37 +183,51 @@ __device__ __forceinline__ void sys_step(SysState<K, DRIFT>& s, const int t, con
 			o_p[sf * 32 + lane] = pp; o_vs[sf * 32 + lane] = vsl; o_vf[sf * 32 + lane] = vfl;
 		}
 	}
+}
+
+// rotate + exchange blocks, common to both compute variants (so the registers the 128-bit loads fill are the ones the next
+// step reads: no copies behind the loads)
+template <int K, bool DRIFT>
+__device__ __forceinline__ void sys_exchange(SysState<K, DRIFT>& s, const float (&vfh_out)[K], const int lane_lo, const SysXchg& x) {
 #pragma unroll
 	for (int k = 0; k < K; k++) s.vf_lo[k] = __shfl_sync(kFull, vfh_out[k], lane_lo);   // the high column-face is the low column-face of lane+1
+	// exchange block, branch-free.  A lane is the LAST column of at most one stage (k31 = 31 - lane) and the FIRST column of
+	// at most one (k0 = (32 - lane) & 31); the ring addresses of those roles were formed by all lanes at once (x.*).  The
+	// float4 hand-over is stored and re-loaded by EVERY lane: the wrap lane stores to the outgoing ring and loads from the
+	// incoming one, every other lane uses a private scratch slot and reads back what it just wrote (same thread, same
+	// address, program order) -- two unpredicated 128-bit accesses and two address selects per stage instead of a
+	// divergent branch (ptxas turns predicated 128-bit shared accesses into branches).
 #pragma unroll
 	for (int k = 0; k < K; k++) {
-		if (lane == ((31 - k) & 31)) {                  // last column of stage k ...
-			float* ro = io_out + ((t - 31 - k) & (kSysRio - 1)) * L::RSF;
-			ro[L::kVfOff + k] = vfh_out[k];
-			if (k < K - 1) {                            // ... and first column of stage k+1: the hand-over crosses the strips
-				*reinterpret_cast<float4*>(ro + 4 * k) = make_float4(s.A_p[k + 1], s.A_vs[k + 1], DRIFT ? s.A_dr[k + 1] : 0.f, __uint_as_float(s.A_cd[k + 1]));
-				const float4 h = *reinterpret_cast<const float4*>(io_in + ((t + 1 - k) & (kSysRio - 1)) * L::RSF + 4 * k);
-				s.A_p[k + 1] = h.x; s.A_vs[k + 1] = h.y; s.A_cd[k + 1] = __float_as_uint(h.w);
-				if (DRIFT) s.A_dr[k + 1] = h.z;
-			}
+		const bool last = x.k31 == k, first = x.k0 == k;
+		sts_if(last, x.out_vf, vfh_out[k]);
+		s.vf_lo[k] = lds_if(first, x.in_vf, s.vf_lo[k]);    // first column: the low column-face comes from the left strip
+		if (k < K - 1) {                                    // the last column of stage k is the first column of stage k+1
+			const unsigned po = last ? x.out_hand : x.scratch, pi = last ? x.in_hand : x.scratch;
+			float hx = s.A_p[k + 1], hy = s.A_vs[k + 1], hz = DRIFT ? s.A_dr[k + 1] : 0.f, hw = __uint_as_float(s.A_cd[k + 1]);
+			asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(po), "f"(hx), "f"(hy), "f"(hz), "f"(hw) : "memory");
+			asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(hx), "=f"(hy), "=f"(hz), "=f"(hw) : "r"(pi) : "memory");
+			s.A_p[k + 1] = hx; s.A_vs[k + 1] = hy; s.A_cd[k + 1] = __float_as_uint(hw);
+			if (DRIFT) s.A_dr[k + 1] = hz;
 		}
-		if (lane == ((32 - k) & 31)) s.vf_lo[k] = io_in[((t + 1 - k) & (kSysRio - 1)) * L::RSF + L::kVfOff + k];   // first column: from the left strip
 	}
 }
 
-// lane 0 spins (bounded) until *pr >= need; a time-out raises the error word.  Returns false if the solve must be abandoned.
-__device__ __forceinline__ bool sys_wait(const int* pr, int need, int* status, int lane) {
-	int ok = 1;
+// Lane 0 spins (bounded) until *pr >= need and returns the value it saw (>= need), or -1 after a time-out (which raises the
+// error word).  No fence on this side: every datum the producer published is read with ld.cg (L2) AFTER the poll -- the
+// loads are issued behind the branch that consumes the polled value -- and the producer's release orders its stores before
+// the progress word.
+__device__ __forceinline__ int sys_wait(const int* pr, int need, int* status, int lane) {
+	int seen = 0;
 	if (lane == 0) {
 		long long spins = 0;
-		while (*((volatile const int*)pr) < need) {
-			if (++spins > (1ll << 24) || ((spins & 255) == 0 && *((volatile const int*)status) != 0)) { ok = 0; break; }
-			__nanosleep(40);
+		while ((seen = *((volatile const int*)pr)) < need) {
+			if (++spins > (1ll << 24) || ((spins & 255) == 0 && *((volatile const int*)status) != 0)) { seen = -1; break; }
+			__nanosleep(20);
 		}
-		if (!ok) atomicExch(status, FLIPGPU_ESTATE);
-		__threadfence();
+		if (seen < 0) atomicExch(status, FLIPGPU_ESTATE);
 	}
-	return __shfl_sync(kFull, ok, 0) != 0;
+	return __shfl_sync(kFull, seen, 0);
 }
 
 template <int K, bool XFAST, bool DRIFT>
@@ -210,6 +246,7 @@ __global__ void __launch_bounds__(32 * kSysWarps, 1) sor_systolic_kernel(SysArgs
 	float* o_vf = o_vs + kSysRin * 32;
 	float* io_in = o_vf + kSysRin * 32;
 	float* io_out = io_in + kSysRio * L::RSF;
+	float* scratch = io_out + kSysRio * L::RSF;
 	const int nf = A.nf, ns = A.ns;
 	const int lane_hi = (lane + 1) & 31, lane_lo = (lane + 31) & 31;
 	const int cK = (lane + K - 1) & 31;            // this lane's position in the strip of the last stage
@@ -279,10 +316,16 @@ __global__ void __launch_bounds__(32 * kSysWarps, 1) sor_systolic_kernel(SysArgs
 			}
 		};
 		bool alive = true;
+		int have_left = dep_left ? 0 : 0x7fffffff, have_prev = dep_prev ? 0 : 0x7fffffff;   // progress of the two producers as last seen
+		long long c_wait = 0, c_flush = 0, c_io = 0, c_step = 0;
+		const long long c_begin = clock64();
 		auto wait_rows = [&](int need) {
 			need = min(need, ns);
-			if (dep_left && alive) alive = sys_wait(dep_left, need, A.status, lane);
-			if (dep_prev && alive) alive = sys_wait(dep_prev, need, A.status, lane);
+			if (have_left >= need && have_prev >= need) return;
+			const long long c0 = clock64();
+			if (have_left < need) { have_left = sys_wait(dep_left, need, A.status, lane); alive = have_left >= 0; }
+			if (alive && have_prev < need) { have_prev = sys_wait(dep_prev, need, A.status, lane); alive = have_prev >= 0; }
+			c_wait += clock64() - c0;
 		};
 
 		// ---- prologue: row 0 directly, rows [1, G+1) into the prefetch registers
@@ -303,23 +346,43 @@ __global__ void __launch_bounds__(32 * kSysWarps, 1) sor_systolic_kernel(SysArgs
 		fetch(1);
 
 		// running slots of this lane: stage-0 rows S0 = t - lane and S0 + 1, last-stage row SK = t - cK - (K-1)
+		SysXchg x;
+		x.k31 = (31 - lane) & 31; x.k0 = (32 - lane) & 31;
+		const unsigned sa_in = (unsigned)__cvta_generic_to_shared(io_in), sa_out = (unsigned)__cvta_generic_to_shared(io_out);
+		x.scratch = (unsigned)__cvta_generic_to_shared(scratch + 4 * lane);
+		x.out_vf = sa_out; x.out_hand = sa_out; x.in_hand = sa_in; x.in_vf = sa_in;
 		int s0 = ((0 - lane) % kSysRin + kSysRin) % kSysRin;
 		int s1 = s0 + 1 == kSysRin ? 0 : s0 + 1;
 		int sf = ((0 - cK - (K - 1)) % kSysRin + 2 * kSysRin) % kSysRin;
-		int flushed = 0;                                    // rows [0, flushed) are final in global memory
+		int flushed = 0, published = 0, pub_tick = 0;       // rows [0, flushed) are stored, rows [0, published) announced
+		auto publish = [&](int rows) {        // release: orders the warp's earlier stores (joined by __syncwarp) before the progress word
+			if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(my_prog), "r"(rows) : "memory");
+			published = rows;
+		};
 
 		auto flush = [&](int done) {          // rows [flushed, done): last-stage results -> grid arrays, ring rows -> global ring
+			// the rows stored at least one phase ago are announced every kSysPubEvery phases (a gpu-scope release costs an L2 round trip)
+			if (flushed > published && (++pub_tick >= kSysPubEvery || done >= ns)) { publish(flushed); pub_tick = 0; }
 			if (done <= flushed) return;
 			__syncwarp();
-			int slot = flushed % kSysRin;
-			for (int S = flushed; S < done; S++) {
-				if (S >= 1 && FK >= 1 && FK <= nf - 1) {
-					const size_t c = (size_t)FK + (size_t)nf * S;
-					if (FK <= nf - 2 && S <= ns - 2) __stcg(A.p + c, o_p[slot * 32 + lane]);
-					if (S <= ns - 2) __stcg(A.vf + c, o_vf[slot * 32 + lane]);
-					if (FK <= nf - 2) __stcg(A.vs + c, o_vs[slot * 32 + lane]);
+			const bool col_ok = FK >= 1 && FK <= nf - 1, col_in = FK <= nf - 2;
+			for (int base = flushed; base < done; base += G) {      // G rows per pass: all shared loads, then all global stores
+				float fp[G], fv[G], fs[G];
+				int slot = base % kSysRin;
+#pragma unroll
+				for (int g = 0; g < G; g++) {
+					fp[g] = o_p[slot * 32 + lane]; fv[g] = o_vf[slot * 32 + lane]; fs[g] = o_vs[slot * 32 + lane];
+					slot = slot + 1 == kSysRin ? 0 : slot + 1;
 				}
-				slot = slot + 1 == kSysRin ? 0 : slot + 1;
+				size_t c = (size_t)FK + (size_t)nf * base;
+#pragma unroll
+				for (int g = 0; g < G; g++, c += nf) {
+					const int S = base + g;
+					if (S >= done || S < 1 || !col_ok) continue;
+					if (col_in && S <= ns - 2) __stcg(A.p + c, fp[g]);
+					if (S <= ns - 2) __stcg(A.vf + c, fv[g]);
+					if (col_in) __stcg(A.vs + c, fs[g]);
+				}
 			}
 			if (ring_out) {
 				const int n4 = (done - flushed) * (L::RSF / 4);
@@ -330,39 +393,51 @@ __global__ void __launch_bounds__(32 * kSysWarps, 1) sor_systolic_kernel(SysArgs
 				}
 			}
 			flushed = done;
-			// release: every lane has stored, the warp converges, then ONE lane fences (cumulative at gpu scope) and publishes
-			__syncwarp();
-			if (lane == 0) {
-				__threadfence();
-				*((volatile int*)my_prog) = done;
-			}
+			__syncwarp();                     // every lane has issued its stores before lane 0 releases them (next phase)
 		};
 
 		for (int t0 = 0; t0 < T; t0 += G) {
 			// ---- phase: publish what is complete, make sure the next-but-one block of rows exists, refill
+			const long long c0 = clock64();
 			flush(min(max(t0 - 30 - K, 0), ns));
+			const long long c1 = clock64();
 			wait_rows(t0 + 2 * G + 1);
 			if (!alive) return;
+			const long long c2 = clock64();
 			land(t0 + 1);                     // rows [t0+1, t0+G+1), fetched one phase ago
 			fetch(t0 + G + 1);                // rows [t0+G+1, t0+2G+1) stay in flight during the G steps below
 			__syncwarp();
-#pragma unroll
+			const long long c3 = clock64();
+			c_flush += c1 - c0; c_io += c3 - c2;
+#pragma unroll kSysStepUnroll
 			for (int g = 0; g < G; g++) {
 				const int t = t0 + g;
 				// fast body unless some active cell of this step has a closed neighbour
 				unsigned any = __float_as_uint(in_cd[s0 * 32 + lane].x);
 #pragma unroll
 				for (int k = 1; k < K; k++) any |= s.B_cd[k];
+				x.out_hand = sa_out + 4u * (unsigned)(((t - 31 - x.k31) & (kSysRio - 1)) * L::RSF + 4 * x.k31);
+				x.out_vf = x.out_hand + 4u * (unsigned)(L::kVfOff - 3 * x.k31);
+				x.in_hand = sa_in + 4u * (unsigned)(((t + 1 - x.k31) & (kSysRio - 1)) * L::RSF + 4 * x.k31);
+				x.in_vf = sa_in + 4u * (unsigned)(((t + 1 - x.k0) & (kSysRio - 1)) * L::RSF + L::kVfOff + x.k0);
+				float vfh_out[K];
 				if (__any_sync(kFull, any & 256u))
-					sys_step<K, XFAST, DRIFT, true>(s, t, lane, lane_hi, lane_lo, in_vf, in_vs, in_p, in_cd, o_p, o_vs, o_vf, io_in, io_out, s0, s1, sf, A.cp, A.omega);
+					sys_compute<K, XFAST, DRIFT, true>(s, vfh_out, lane, lane_hi, in_vf, in_vs, in_p, in_cd, o_p, o_vs, o_vf, s0, s1, sf, A.cp, A.omega);
 				else
-					sys_step<K, XFAST, DRIFT, false>(s, t, lane, lane_hi, lane_lo, in_vf, in_vs, in_p, in_cd, o_p, o_vs, o_vf, io_in, io_out, s0, s1, sf, A.cp, A.omega);
+					sys_compute<K, XFAST, DRIFT, false>(s, vfh_out, lane, lane_hi, in_vf, in_vs, in_p, in_cd, o_p, o_vs, o_vf, s0, s1, sf, A.cp, A.omega);
+				sys_exchange<K, DRIFT>(s, vfh_out, lane_lo, x);
 				s0 = s1;
 				s1 = s1 + 1 == kSysRin ? 0 : s1 + 1;
 				sf = sf + 1 == kSysRin ? 0 : sf + 1;
 			}
+			c_step += clock64() - c3;
 		}
 		flush(ns);
+		publish(ns);
+		if (A.prof && lane == 0) {
+			atomicAdd(A.prof + 0, (unsigned long long)c_wait); atomicAdd(A.prof + 1, (unsigned long long)c_flush); atomicAdd(A.prof + 2, (unsigned long long)c_io);
+			atomicAdd(A.prof + 3, (unsigned long long)c_step); atomicAdd(A.prof + 4, 1ull); atomicAdd(A.prof + 5, (unsigned long long)(clock64() - c_begin));
+		}
 	}
 }
 
@@ -379,14 +454,22 @@ struct SysWorkspace {
 	int* counter = nullptr;
 	int* status = nullptr;
 	int* h_status = nullptr;
+	unsigned long long* prof = nullptr;
 	int sms = 0;
 };
 
 void sys_workspace_free(SysWorkspace* w) {
 	if (!w) return;
-	cudaFree(w->cd); cudaFree(w->ring); cudaFree(w->tasks); cudaFree(w->prog); cudaFree(w->counter); cudaFree(w->status);
+	cudaFree(w->cd); cudaFree(w->ring); cudaFree(w->tasks); cudaFree(w->prog); cudaFree(w->counter); cudaFree(w->status); cudaFree(w->prof);
 	if (w->h_status) cudaFreeHost(w->h_status);
 	delete w;
+}
+int sys_workspace_profile(SysWorkspace* w, unsigned long long out[8]) {
+	for (int i = 0; i < 8; i++) out[i] = 0;
+	if (!w || !w->prof) return FLIPGPU_ESTATE;
+	FG_CUDA(cudaMemcpy(out, w->prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	FG_CUDA(cudaMemset(w->prof, 0, 8 * sizeof(unsigned long long)));
+	return FLIPGPU_OK;
 }
 int sys_workspace_check(SysWorkspace* w) {
 	if (!w || !w->h_status || *w->h_status == 0) return FLIPGPU_OK;
@@ -436,7 +519,7 @@ static int sys_launch(SysWorkspace* w, const SorGrid& g, int chunks, float cp, f
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
 	SysArgs A;
 	A.nf = g.nf; A.ns = g.ns; A.nw = nw; A.nq = chunks; A.vf = g.vel_f; A.vs = g.vel_s; A.p = g.p; A.cd = w->cd; A.tasks = w->tasks;
-	A.n_tasks = n_tasks; A.counter = w->counter; A.prog = w->prog; A.status = w->status; A.ring = w->ring; A.cp = cp; A.omega = omega;
+	A.n_tasks = n_tasks; A.counter = w->counter; A.prog = w->prog; A.status = w->status; A.ring = w->ring; A.cp = cp; A.omega = omega; A.prof = w->prof;
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_systolic_kernel<K, true, true> : (const void*)sor_systolic_kernel<K, true, false>)
 	                          : (use_drift ? (const void*)sor_systolic_kernel<K, false, true> : (const void*)sor_systolic_kernel<K, false, false>);
 	const size_t smem = (size_t)kSysWarps * L::kWarpFloats * 4;
@@ -465,6 +548,10 @@ int sor_solve_systolic(SysWorkspace** wsp, const SorGrid& g, int iters, float cp
 			FG_CUDA(cudaMallocHost(&w->h_status, 4));
 			*w->h_status = 0;
 			w->sms = num_sms();
+			if (getenv("FLIPGPU_SOR_PROFILE")) {
+				FG_CUDA(cudaMalloc(&w->prof, 8 * sizeof(unsigned long long)));
+				FG_CUDA(cudaMemset(w->prof, 0, 8 * sizeof(unsigned long long)));
+			}
 		}
 	}
 	const bool use_drift = drift && g.density && g.rest;

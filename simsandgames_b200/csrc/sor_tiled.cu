@@ -1,5 +1,4 @@
-// Blocked-wavefront Gauss-Seidel SOR in shared memory (FLIP_SOLVER_LEX_TILED; the default lexicographic solver is the
-// register-systolic kernel of sor_systolic.cu, this one is kept as an independent cross-check): the reference's lexicographic sweep order
+// Blocked-wavefront Gauss-Seidel SOR in shared memory (FLIP_SOLVER_LEX_WAVEFRONT, the default): the reference's lexicographic sweep order
 // (flip_fluid.h:458-494 / fluid.h:106-138), bit for bit, staged through shared memory with
 // temporal blocking, as ONE persistent kernel per solve.
 //
@@ -277,7 +276,7 @@ struct SorWorkspace {
 	unsigned char* act = nullptr;  // activity of the unskewed TxT squares
 	int na = 0, nb = 0;
 	unsigned long long* prof = nullptr;
-	SysWorkspace* sys = nullptr;  // workspace of the register-systolic kernel (sor_systolic.cu), the default lexicographic solver
+	SysWorkspace* sys = nullptr;  // workspace of the register-systolic kernel (sor_systolic.cu, FLIP_SOLVER_LEX_SYSTOLIC)
 	int sms = 0;
 	int* status = nullptr;    // device error word raised by a dependency wait that timed out ...
 	int* h_status = nullptr;  // ... mirrored into pinned host memory behind every solve launch
@@ -286,6 +285,7 @@ struct SorWorkspace {
 // diagnostic: cycles spent per tile phase (enabled by FLIPGPU_SOR_PROFILE=1 in the environment at plan time)
 int sor_workspace_profile(SorWorkspace* w, unsigned long long out[8]) {
 	for (int i = 0; i < 8; i++) out[i] = 0;
+	if (w && w->sys && sys_workspace_profile(w->sys, out) == FLIPGPU_OK && out[4] != 0) return FLIPGPU_OK;   // the systolic kernel ran
 	if (!w || !w->prof) return FLIPGPU_ESTATE;
 	FG_CUDA(cudaMemcpy(out, w->prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	out[5] = (unsigned long long)w->n_tiles; out[6] = (unsigned long long)w->kc; out[7] = (unsigned long long)w->nq;

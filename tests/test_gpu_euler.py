@@ -54,7 +54,7 @@ def test_device_set_obstacle_bit_exact(tunnel):
         assert_bit_equal(sim.readback(n), getattr(o, n), f"after setObstacle {n}")
 
 
-@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL, sg.LEX_TILED])
+@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL, sg.LEX_SYSTOLIC])
 def test_projection_wavefront_bit_identical(tunnel, order):
     o = co.make_euler_scene(96, 72, oracle_kind="port")
     for n in ("u", "v", "m", "solid"):

@@ -158,7 +158,7 @@ def test_g2p_bit_exact(tank_states, step):
     assert_bit_equal(sim.readback("particle_vel"), o.particle_vel[:2 * P], "F8 vel")  # gather: same arithmetic, bit-exact
 
 
-@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL, sg.LEX_TILED])
+@pytest.mark.parametrize("order", [sg.LEX_WAVEFRONT, sg.LEX_DIAGONAL, sg.LEX_SYSTOLIC])
 @pytest.mark.parametrize("step", [0, 29, 60])
 def test_solver_wavefront_bit_identical(tank_states, step, order):
     """F9 parity mode: the anti-diagonal schedule (blocked in shared memory, or one diagonal per grid sync)
