@@ -117,6 +117,25 @@ def run_cpu_reference(n_sample, steps, warmup):
 
 
 
+def run_cpu_reference_full_size(n=BENCH_N, steps=1):
+    """the reference's own CPU step on the FULL benchmark config (4096^2 cells / 64 264 080 particles), one
+    step from the initial state (about 80 s on one host core; the reference is strictly serial)."""
+    from oracle import cpu_oracle as co
+    kind = co.best_kind("flip")
+    o, p, g = co.make_flip_scene("synthetic", N=n, oracle_kind=kind)
+    P = o.num_particles
+    t0 = time.perf_counter()
+    ph = o.simulate(**p, n_steps=steps, timed=True)
+    dt = time.perf_counter() - t0
+    interior = (o.f_num_x - 2) * (o.f_num_y - 2)
+    out = dict(kind="reference" if kind == "ref" else "port", grid=[o.f_num_x, o.f_num_y], particles=P, steps=steps, seconds_per_step=dt / steps,
+               value=P * steps / dt, unit=UNIT, cores=1, cell_updates_per_s=interior * p["num_pressure_iters"] * steps / (ph[5] * 1e-9),
+               phase_share={k: round(v / sum(ph), 4) for k, v in zip(("integrate", "pushApart", "collide", "p2g", "density", "solve", "g2p", "colours"), ph)},
+               sample=f"the full BASELINE configs[2] scene, step 1 from the initial lattice, 1 thread")
+    o.close() if hasattr(o, "close") else None
+    return out
+
+
 def run_cpu_reference_euler(n_sample=1024, iters=100):
     """eulerian_fluid's CPU step (oracle/_ref = unmodified fluid.h; else the C port) on a bounded sample of BASELINE
     configs[1], timed with and without flush-to-zero/denormals-are-zero: SURVEY Q17 -- the reference stalls on denormals
@@ -325,6 +344,62 @@ def sharded_flip_bench(args, rank, world, local_rank):
     return info
 
 
+def shard_selfcheck(rank, world, local_rank, steps=6):
+    """Before anything is timed: the default tank (BASELINE configs[0] scene) stepped by the slab-sharded path over `world` ranks must
+    equal the one-GPU red-black run bit for bit -- every particle, u, v, p and the cell types.  Returns "bit-identical" or raises."""
+    import numpy as np
+    import torch.distributed as dist
+    import simsandgames_b200 as sg
+    from simsandgames_b200 import parallel
+    one, kw, g = sg.scenes.make_flip_tank("default", device=local_rank)
+    P = one.num_particles
+    pos0 = one.readback("particle_pos").reshape(-1, 2).copy()
+    s0 = one.readback("s").copy()
+    rest = None
+    if rank == 0:
+        one.simulate(**kw, n_steps=1, solver_order=sg.RED_BLACK, update_colors=False)   # latch the rest density on one GPU, then restart
+        rest = float(one.particle_rest_density)
+        one.upload("particle_pos", pos0.reshape(-1)); one.upload("particle_vel", np.zeros(2 * P, np.float32))
+        for n in ("u", "v", "prev_u", "prev_v", "p", "particle_density"):
+            one.upload(n, np.zeros(one.f_num_cells, np.float32))
+        one.simulate(**kw, n_steps=steps, solver_order=sg.RED_BLACK, update_colors=False)
+    box = [rest]
+    dist.broadcast_object_list(box, src=0)
+    rest = box[0]
+    uid = parallel.broadcast_unique_id()
+    sh = sg.FlipFluidSharded(g["density"], g["width"], g["height"], g["spacing"], g["radius"], 2 * P, P, rank, world, unique_id=uid, device=local_rank)
+    sh.upload("s", s0)
+    sh.particle_rest_density = rest
+    mine = sh.owns(pos0)
+    sh.upload_particles(pos0[mine], None, np.flatnonzero(mine).astype(np.int32))
+    sh.simulate(**kw, n_steps=steps)
+    p_, v_, i_ = sh.readback_particles()
+    part = dict(pos=p_, vel=v_, ids=i_, u=sh.readback_own_rows("u"), v=sh.readback_own_rows("v"), p=sh.readback_own_rows("p"), ct=sh.readback_own_rows("cell_type"))
+    parts = [None] * world
+    dist.all_gather_object(parts, part)
+    sh.close()
+    verdict = "bit-identical"
+    if rank == 0:
+        ids = np.concatenate([q["ids"] for q in parts])
+        ok = np.array_equal(np.sort(ids), np.arange(P))
+        if ok:
+            pos = np.empty((P, 2), np.float32); vel = np.empty((P, 2), np.float32)
+            pos[ids] = np.concatenate([q["pos"] for q in parts]).reshape(-1, 2)
+            vel[ids] = np.concatenate([q["vel"] for q in parts]).reshape(-1, 2)
+            ok = (np.array_equal(pos.view(np.int32).reshape(-1), one.readback("particle_pos").view(np.int32)) and
+                  np.array_equal(vel.view(np.int32).reshape(-1), one.readback("particle_vel").view(np.int32)))
+            for key, name in (("u", "u"), ("v", "v"), ("p", "p"), ("ct", "cell_type")):
+                got = np.concatenate([q[key] for q in parts], axis=0).reshape(-1)
+                ok = ok and np.array_equal(got.view(np.int32), one.readback(name).view(np.int32))
+        verdict = "bit-identical" if ok else "MISMATCH"
+    one.close()
+    box = [verdict]
+    dist.broadcast_object_list(box, src=0)
+    if box[0] != "bit-identical":
+        raise SystemExit(f"bench.py: the {world}-rank sharded step differs from the one-GPU red-black run on the default tank -- no line is printed")
+    return box[0]
+
+
 def synthetic_rank_lattice(N, j0, j1, build=True):
     """The particles of the synthetic dam-break (SURVEY 8d rule; lattice of flip_fluid/src/main.cpp:47-66) whose cell row lies
     in grid rows [j0, j1), with their global caller indices p = i*num_y + j -- without materialising the other ranks' particles.
@@ -355,14 +430,17 @@ def synthetic_rank_lattice(N, j0, j1, build=True):
     return out
 
 
-def s3_bench(args, rank, world, local_rank, N=16384):
-    """BASELINE configs[3]: ONE flip_fluid dam-break of N^2 = 16384^2 cells / 1 029 824 840 particles, slab-sharded over `world`
-    GPUs (a fixed global problem: ranks holding air own few particles).  Every rank builds only its own lattice rows."""
+def single_tank_sharded(args, rank, world, local_rank, N, with_obstacle=False, steps=None):
+    """ONE flip_fluid dam-break of N^2 cells (SURVEY 8d rule), slab-sharded over `world` GPUs -- a fixed global problem, so ranks
+    holding air own few particles.  BASELINE configs[3] (N=16384, 1 029 824 840 particles, 50 sweeps) and configs[4] (N=8192 with
+    the disc obstacle, 200 sweeps).  Every rank builds only its own lattice rows.  Returns the result dict on rank 0 (None elsewhere)."""
     import numpy as np
     import torch
     import torch.distributed as dist
     import simsandgames_b200 as sg
     from simsandgames_b200 import parallel
+    steps = steps or args.steps
+    iters = 200 if with_obstacle else 50
     uid = parallel.broadcast_unique_id()
     j0, j1 = parallel.slab_partition(N, world)[rank]
     geo = synthetic_rank_lattice(N, j0, j1, build=False)
@@ -382,14 +460,19 @@ def s3_bench(args, rank, world, local_rank, N=16384):
     if w1 == N: s[-1] = 0
     sim.upload_rows("s", s, w0)
     del s
-    kw = dict(dt=dt, gravity=9.81, flip_ratio=0.9, num_pressure_iters=50, num_particle_iters=2, over_relaxation=1.9, compensate_drift=True,
-              separate_particles=True, obstacle_x=0.0, obstacle_y=0.0, obstacle_vel_x=0.0, obstacle_vel_y=0.0, obstacle_radius=0.0)
+    ox = oy = orad = 0.0
+    if with_obstacle:   # static disc of the S4 rule through the device setObstacle (main.cpp:104-122 incl. its loop bounds)
+        f32 = np.float32
+        ox, oy, orad = float(f32(.75) * W), float(f32(.67) * W), float(f32(.05) * W)
+        sim.set_obstacle(ox, oy, 0.0, 0.0, orad)
+    kw = dict(dt=dt, gravity=9.81, flip_ratio=0.9, num_pressure_iters=iters, num_particle_iters=2, over_relaxation=1.9, compensate_drift=True,
+              separate_particles=True, obstacle_x=ox, obstacle_y=oy, obstacle_vel_x=0.0, obstacle_vel_y=0.0, obstacle_radius=orad)
     stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
     sim.simulate(**kw, n_steps=args.warmup)
     sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    sim.simulate(**kw, n_steps=args.steps)
+    sim.simulate(**kw, n_steps=steps)
     e1.record(stream)
     sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -401,21 +484,59 @@ def s3_bench(args, rank, world, local_rank, N=16384):
     dist.all_gather_object(owned, n_now)
     assert int(cnt[0].item()) == P_global == int(cnt[1].item()), "particles lost or duplicated across ranks"
     mem = torch.cuda.mem_get_info(local_rank)
-    if rank == 0:
-        peak, peak_src = peaks()
-        s_per_step = ms * 1e-3 / args.steps
-        step_bytes = 140.0 * P_global + (96.0 + 36.0 * 50) * float(N) * N
-        print(json.dumps({
-            "metric": METRIC, "value": P_global / s_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"flip_fluid synthetic dam-break {N}^2 grid, {P_global} particles, 50 SOR iters, slab-sharded (BASELINE configs[3])",
+    sim.close()
+    del h_out
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    s_per_step = ms * 1e-3 / steps
+    step_bytes = 140.0 * P_global + (96.0 + 36.0 * iters) * float(N) * N
+    name = "configs[4]" if with_obstacle else "configs[3]"
+    return {"metric": METRIC, "value": P_global / s_per_step, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "cell_updates_per_s_whole_step": float(N - 2) * (N - 2) * iters / s_per_step,
+            "config": {"workload": f"flip_fluid synthetic dam-break {N}^2 grid, {P_global} particles, {iters} SOR iters" +
+                                   (", static disc obstacle" if with_obstacle else "") + f", slab-sharded (BASELINE {name})",
                        "grid": [N, N], "particles_per_gpu": owned, "solver_order": "red_black", "parallelism": f"y-slabs over {world} GPUs, NCCL halo/ghost exchange",
                        "gpu_mem_used_GB_rank0": round((mem[1] - mem[0]) / 1e9, 1)},
             "roofline": {"bound": "hbm", "kernel": "whole sharded step (all GPUs)", "achieved": step_bytes / s_per_step / 1e9 / world, "peak": peak,
-                         "unit": "GB/s per GPU", "frac": step_bytes / s_per_step / 1e9 / world / peak, "traffic": None, "peak_source": peak_src},
-        }), flush=True)
-    sim.close()
+                         "unit": "GB/s per GPU", "frac": step_bytes / s_per_step / 1e9 / world / peak, "traffic": None, "peak_source": peak_src}}
+
+
+def s3_bench(args, rank, world, local_rank, N=16384):
+    import torch.distributed as dist
+    line = single_tank_sharded(args, rank, world, local_rank, N)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     dist.destroy_process_group()
+
+
+def s4_single_gpu(local_rank, steps=4, warmup=3, N=8192):
+    """BASELINE configs[4] on ONE GPU: 8192^2 cells with the disc obstacle, 257 311 935 particles, 200 SOR iterations per step."""
+    import torch
+    import simsandgames_b200 as sg
+    sim, kw, geo = sg.scenes.make_flip_tank("synthetic", N=N, with_obstacle=True, device=local_rank)
+    P, nx, ny, iters = sim.num_particles, sim.f_num_x, sim.f_num_y, kw["num_pressure_iters"]
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+    sim.simulate(**kw, n_steps=warmup, update_colors=False)
+    sim.synchronize()
+    sim.enable_timings(True); sim.reset_timings()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.simulate(**kw, n_steps=steps, update_colors=False)
+    e1.record(stream)
+    sim.synchronize(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ph = {k: v / steps for k, v in sim.timings().items()}
+    sim.enable_timings(False)
+    assert bool((sim.readback("particle_pos")[:4096] == sim.readback("particle_pos")[:4096]).all())   # finite
+    sim.close()
+    peak, _ = peaks()
+    step_bytes = 140.0 * P + (96.0 + 36.0 * iters) * float(nx) * ny
+    return {"workload": f"flip_fluid synthetic dam-break {N}^2 grid with static disc obstacle, {P} particles, {iters} SOR iters (BASELINE configs[4]), 1 GPU, steps {warmup + 1}-{warmup + steps}",
+            "ms_per_step": ms, "value": P / (ms * 1e-3), "unit": UNIT, "cell_updates_per_s": float(nx - 2) * (ny - 2) * iters / (ph["solve"] * 1e-3),
+            "phase_ms_per_step": ph, "solver_order": "lexicographic (blocked wavefront)",
+            "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms * 1e-3) / 1e9, "frac_of_measured": step_bytes / (ms * 1e-3) / 1e9 / peak}}
 
 
 def reference_arm(args, rank, world):
@@ -459,8 +580,21 @@ def product_arm(args, rank, world, local_rank):
         s3_bench(args, rank, world, local_rank, N=16384 if args.grid == BENCH_N else args.grid)
         return
     if world > 1:
+        selfcheck = shard_selfcheck(rank, world, local_rank)      # fails the run (no line) unless bit-identical
         info = sharded_flip_bench(args, rank, world, local_rank)
         shard = sharded_solver_bench(rank, world, local_rank)
+        extra = {}
+        if not args.no_extra_legs:
+            # BASELINE configs[4] as a full sharded step (8192^2 + obstacle, 200 sweeps), and configs[3] (16384^2, 1.03e9 particles) where it fits
+            for key, n_grid, obst, min_world in (("s4_8192_obstacle_sharded", 8192, True, 2), ("s3_16384_sharded", 16384, False, 4)):
+                if world < min_world:
+                    continue
+                try:
+                    extra[key] = single_tank_sharded(args, rank, world, local_rank, n_grid, with_obstacle=obst, steps=4)
+                except SystemExit:
+                    raise
+                except Exception as exc:
+                    extra[key] = {"error": str(exc)[:300]}
         if rank == 0:
             peak, peak_src = peaks()
             N = args.grid
@@ -488,7 +622,10 @@ def product_arm(args, rank, world, local_rank):
                              "frac": step_bytes / world / s_per_step / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                              "formula": "140*P + (96+36*iters)*C per GPU (SURVEY 8d)"},
                 "sharded_solver": shard,
+                "shard_selfcheck": selfcheck,
+                "shard_selfcheck_what": f"default tank, 6 steps: {world}-rank sharded run vs one-GPU red-black run, particle_pos/vel, u, v, p, cell_type compared bitwise before the timed region",
             }
+            line.update({k: v for k, v in extra.items() if v is not None})
             if info.get("phase_ms_per_step"):
                 line["phase_ms_per_step"] = info["phase_ms_per_step"]
             print(json.dumps(line), flush=True)
@@ -593,7 +730,7 @@ def product_arm(args, rank, world, local_rank):
     # ---- end to end through the C ABI with HOST buffers (pinned): per step, the caller's per-frame writes go H2D
     #      (the s field that FluidUI::setObstacle rewrites every frame, main.cpp:106-122) and the array the caller
     #      reads every frame comes back D2H (particle_pos, main.cpp:173-176), in caller particle order.
-    e2e_steps = max(4, min(args.steps, 8))
+    e2e_steps = max(8, args.steps)   # the last frame's PCIe copy is not hidden by a next step: it is part of the measurement
     h_frames = [torch.empty(2 * P, dtype=torch.float32).pin_memory() for _ in range(2)]   # double-buffered frames
     h_pos = h_frames[0]
     reseed()
@@ -689,6 +826,11 @@ def product_arm(args, rank, world, local_rank):
         line["sharded_solver"] = shard
     if world == 1:
         line["eulerian_s1"] = eulerian_bench(local_rank)
+    if world == 1 and not args.no_extra_legs and N == BENCH_N:
+        try:
+            line["s4_8192_obstacle"] = s4_single_gpu(local_rank)
+        except Exception as exc:
+            line["s4_8192_obstacle"] = {"error": str(exc)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         line["eulerian_s1"]["cpu_baseline"] = run_cpu_reference_euler()
         n_sample = 1024
@@ -698,6 +840,11 @@ def product_arm(args, rank, world, local_rank):
             "sample": f"same dam-break rule at {n_sample}^2 cells / {r['particles']} particles, 3 steps, 1 thread of {os.cpu_count()} host CPUs "
                       f"({r['seconds']:.1f} s; the reference is serial)",
             "cell_updates_per_s": r["cell_updates_per_s"], "phase_share": r["phase_share"]}
+        if not args.no_full_size_cpu and N == BENCH_N:
+            try:
+                line["cpu_baseline"]["full_size"] = run_cpu_reference_full_size()
+            except Exception as exc:   # e.g. not enough host memory: report, never break the line
+                line["cpu_baseline"]["full_size"] = {"error": str(exc)[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -711,6 +858,8 @@ def main():
     ap.add_argument("--impl", default="flipgpu", choices=["flipgpu", "reference"])
     ap.add_argument("--grid", type=int, default=BENCH_N, help="cells per side of the synthetic dam-break (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-size-cpu", action="store_true", help="skip the one full-size (4096^2) step of the CPU reference (~80 s)")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the S4 (8192^2 + obstacle) / S3 legs")
     ap.add_argument("--s3", action="store_true", help="N>1 only: BASELINE configs[3], one 16384^2 / 1.03e9-particle tank sharded over the ranks")
     ap.add_argument("--with-shard-bench", action="store_true", help="also run the sharded-solver leg at N=1 (always run for N>1)")
     args = ap.parse_args()

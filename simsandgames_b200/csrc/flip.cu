@@ -415,6 +415,12 @@ __global__ void __launch_bounds__(kThreads) k_check_s_binary(size_t n, const flo
 	if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;  // racing writers store the same value
 }
 
+// One word device -> pinned host memory, written by a kernel: a cudaMemcpyAsync D2H of 4 bytes on the simulation stream
+// queues on the D2H copy engine BEHIND a frame that is crossing PCIe (9 ms at S2) and stalls every kernel behind it.
+__global__ void k_word_to_host(const int* __restrict__ d_word, volatile int* __restrict__ h_word) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) *h_word = *d_word;
+}
+
 // ------------------------------------------------------------------ F4 + F5 marking
 // handleParticleCollisions (flip_fluid.h:254-289) fused with the fluid-cell marking of :352-359 and with
 // the key + histogram of the second (index-only) counting sort: particles by the BASE CELL (x0,y0) of their
@@ -590,12 +596,17 @@ __global__ void k_rest_latch(int n_partials, const float* __restrict__ partials,
 // :406-409 are taken from the stencil's own nodes where they coincide:
 // cell_type[n1-1] is node 0 and cell_type[n2-1] is node 3 whenever x1 == x0+1, cell_type[n3-nx] is node 0 and
 // cell_type[n2-nx] is node 1 whenever y1 == y0+1 (they differ only in the aliased last column / row, Q13).
+// STAGE: the frame pipeline's caller-order copy of the (final) positions is written from here -- the kernel is bound by
+// gather latency, not bandwidth, so the scattered 8-byte stores ride along (a separate un-permute pass costs 1.46 ms at S2).
+template <bool STAGE>
 __global__ void __launch_bounds__(kThreads) k_g2p(Geo g, const float2* __restrict__ pos, float2* __restrict__ vel,
                                                   const float* __restrict__ u, const float* __restrict__ v,
                                                   const float* __restrict__ prev_u, const float* __restrict__ prev_v,
-                                                  const int* __restrict__ cell_type, float flip_ratio) {
+                                                  const int* __restrict__ cell_type, float flip_ratio,
+                                                  const int* __restrict__ orig, float2* __restrict__ staging) {
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
 		float2 p = pos[t];
+		if (STAGE) staging[orig[t]] = p;
 		float2 pv = vel[t];
 		Stencil st = make_stencil(g, p.x, p.y);
 		const int n0 = st.x0 + g.nx * st.y0, n1 = st.x1 + g.nx * st.y0, n2 = st.x1 + g.nx * st.y1, n3 = st.x0 + g.nx * st.y1;
@@ -936,17 +947,23 @@ struct FlipSim {
 	float* d_partials = nullptr;
 	float* h_pinned = nullptr;  // [0] rest mirror
 	// asynchronous readback of particle_pos (render thread consumes frame k while frame k+1 is computed)
-	// Frame pipeline.  Once the caller has asked for a frame, every flip_step un-permutes the positions into a staging buffer
-	// (caller order) on a second stream as soon as they are final -- right after the collision pass, i.e. while P2G, the
-	// pressure solve and G2P are still running -- and flip_readback_pos_async only queues the PCIe copy, on a third stream.
-	// Two staging buffers: frame k+1 is staged while frame k is still crossing PCIe.
-	cudaStream_t st_copy = nullptr, st_scatter = nullptr;
-	cudaEvent_t ev_pos_final = nullptr, ev_staged[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	// Frame pipeline.  Once the caller has asked for a frame, the last G2P kernel of every flip_step also writes the positions
+	// in caller order into a staging buffer, and flip_readback_pos_async only queues the PCIe copy, on a second stream.
+	// Two staging buffers: frame k+1 is staged while frame k is still crossing PCIe.  (Un-permuting on a side stream right
+	// after the collision pass, concurrently with the pressure solve, was measured and dropped: the persistent solver kernel
+	// lost 3.5 ms to the contention -- profiles/r2_e2e.md.)
+	cudaStream_t st_copy = nullptr;
+	cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+	// flip_upload_async of the grid fields the caller rewrites every frame (s, u, v): the H2D copy runs on its own stream,
+	// behind everything queued so far (the readers of the old values), and the step joins it only where those fields are
+	// first read (collision / marking pass) -- it hides behind integrate + binning + separation
+	cudaStream_t st_up = nullptr;
+	cudaEvent_t ev_fence = nullptr, ev_uploaded = nullptr;
+	bool upload_pending = false;
 	float2* staging[2] = {nullptr, nullptr};
 	bool copy_pending[2] = {false, false};
 	bool frame_mode = false;     // set by the first flip_readback_pos_async
 	bool staged_valid = false;   // staging[frame_idx] holds the caller-order positions of the current state
-	bool staged_unjoined = false;  // the simulation stream has not yet been ordered behind the last staging pass
 	int frame_idx = 0;
 	SorWorkspace* ws = nullptr;
 	// slab sharding (flip_create_sharded): rank owns grid rows [j0, j1); arrays keep the global size, only the window is processed
@@ -1015,31 +1032,42 @@ int ensure_cell_colors(FlipSim* f) {
 	return FLIPGPU_OK;
 }
 
-// ---- frame pipeline (see FlipSim).  stage_positions: caller-order copy of the CURRENT positions into the next staging buffer,
-// on the scatter stream, ordered behind everything queued on the simulation stream so far.
+// ---- frame pipeline (see FlipSim).  next_staging: the buffer the next frame goes into (allocated on first use; the
+// simulation stream is ordered behind the PCIe copy that may still be reading it -- two frames ago).
+int next_staging(FlipSim* f, int* b_out) {
+	const int b = 1 - f->frame_idx;
+	if (!f->staging[b]) FG_CUDA(cudaMalloc(&f->staging[b], (size_t)std::max(f->d.max_particles, 1) * sizeof(float2)));
+	if (f->copy_pending[b]) FG_CUDA(cudaStreamWaitEvent(f->st, f->ev_copied[b], 0));
+	*b_out = b;
+	return FLIPGPU_OK;
+}
+int staged(FlipSim* f, int b) {
+	FG_CUDA(cudaEventRecord(f->ev_staged[b], f->st));
+	f->frame_idx = b;
+	f->staged_valid = true;
+	return FLIPGPU_OK;
+}
+// stand-alone un-permute (a frame is asked for that the last step did not stage)
 int stage_positions(FlipSim* f) {
 	const int np = f->d.num_particles;
 	if (np == 0) return FLIPGPU_OK;
-	const int b = 1 - f->frame_idx;
-	if (!f->staging[b]) FG_CUDA(cudaMalloc(&f->staging[b], (size_t)std::max(f->d.max_particles, 1) * sizeof(float2)));
-	FG_CUDA(cudaEventRecord(f->ev_pos_final, f->st));
-	FG_CUDA(cudaStreamWaitEvent(f->st_scatter, f->ev_pos_final, 0));
-	if (f->copy_pending[b]) FG_CUDA(cudaStreamWaitEvent(f->st_scatter, f->ev_copied[b], 0));  // that buffer is still crossing PCIe
-	if (f->identity) FG_CUDA(cudaMemcpyAsync(f->staging[b], f->pos[f->cur], (size_t)np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st_scatter));
-	else { k_scatter_to_caller<float2, 1><<<pgrid(f), kThreads, 0, f->st_scatter>>>(np, f->orig[f->cur], f->pos[f->cur], f->staging[b]); f->lc.n++; }
+	int b = 0;
+	FG_TRY(next_staging(f, &b));
+	if (f->identity) FG_CUDA(cudaMemcpyAsync(f->staging[b], f->pos[f->cur], (size_t)np * sizeof(float2), cudaMemcpyDeviceToDevice, f->st));
+	else { k_scatter_to_caller<float2, 1><<<pgrid(f), kThreads, 0, f->st>>>(np, f->orig[f->cur], f->pos[f->cur], f->staging[b]); f->lc.n++; }
 	FG_CUDA(cudaGetLastError());
-	FG_CUDA(cudaEventRecord(f->ev_staged[b], f->st_scatter));
-	f->frame_idx = b;
-	f->staged_valid = true;
-	f->staged_unjoined = true;
+	return staged(f, b);
+}
+// Call before anything changes positions / slot order: the staged frame no longer matches the state afterwards.
+int positions_will_change(FlipSim* f) {
+	f->staged_valid = false;
 	return FLIPGPU_OK;
 }
-// Call before anything on the simulation stream writes positions / slot order: the staging pass must have read them first,
-// and the staged frame no longer matches the state afterwards.
-int positions_will_change(FlipSim* f) {
-	if (f->staged_unjoined) FG_CUDA(cudaStreamWaitEvent(f->st, f->ev_staged[f->frame_idx], 0));
-	f->staged_unjoined = false;
-	f->staged_valid = false;
+
+// order the simulation stream behind the uploads queued on the upload stream
+int join_uploads(FlipSim* f) {
+	if (f->upload_pending) FG_CUDA(cudaStreamWaitEvent(f->st, f->ev_uploaded, 0));
+	f->upload_pending = false;
 	return FLIPGPU_OK;
 }
 
@@ -1212,6 +1240,7 @@ int separate(FlipSim* f, int iters, bool colors) {
 
 int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad) {
 	Geo g = geo(f);
+	FG_TRY(join_uploads(f));   // s (cell types), u, v (solid restore of the P2G) are read from here on
 	if (collide) FG_TRY(positions_will_change(f));
 	const size_t goff = (size_t)g.nx * g.gy0;
 	int c = f->cur, C = g.nx * (g.gy1 - g.gy0);
@@ -1265,13 +1294,13 @@ int p2g(FlipSim* f) {
 	} else if (!f->rest_seen && f->exact_order) {
 		k_rest_latch_serial<<<1, 32, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest);
 		f->lc.n++;
-		FG_CUDA(cudaMemcpyAsync(f->h_pinned, f->d_rest, sizeof(float), cudaMemcpyDeviceToHost, f->st));
+		k_word_to_host<<<1, 32, 0, f->st>>>((const int*)f->d_rest, (volatile int*)f->h_pinned);
 	} else if (!f->rest_seen) {
 		k_rest_partials<<<kPartials, 256, 0, f->st>>>(f->d.f_num_cells, f->cell_type, f->dens, f->d_rest, f->d_partials);
 		k_rest_latch<<<1, 32, 0, f->st>>>(kPartials, f->d_partials, f->d_rest);
 		f->lc.n += 2;
 		// mirror the scalar into pinned memory; once a later call sees it non-zero the latch kernels stop
-		FG_CUDA(cudaMemcpyAsync(f->h_pinned, f->d_rest, sizeof(float), cudaMemcpyDeviceToHost, f->st));
+		k_word_to_host<<<1, 32, 0, f->st>>>((const int*)f->d_rest, (volatile int*)f->h_pinned);
 	}
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
@@ -1293,16 +1322,16 @@ int ensure_alt(FlipSim* f) {
 	return FLIPGPU_OK;
 }
 // s was written by the caller: check on the device (asynchronously) whether it is still 0/1-valued
-int queue_s_check(FlipSim* f, size_t first_cell, size_t n_cells, bool whole_array) {
+int queue_s_check(FlipSim* f, size_t first_cell, size_t n_cells, bool whole_array, cudaStream_t st) {
 	if (n_cells == 0) return FLIPGPU_OK;
 	// a whole-array upload starts from scratch; a partial one adds to what is known (or still being checked) about the rest
-	if (whole_array) FG_CUDA(cudaMemsetAsync(f->d_sflag, 0, sizeof(int), f->st));
-	else if (!f->s_check_pending) FG_CUDA(cudaMemsetAsync(f->d_sflag, f->s_binary ? 0 : 0xff, sizeof(int), f->st));
-	k_check_s_binary<<<wave_grid(n_cells, kThreads), kThreads, 0, f->st>>>(n_cells, f->s + first_cell, f->d_sflag);
+	if (whole_array) FG_CUDA(cudaMemsetAsync(f->d_sflag, 0, sizeof(int), st));
+	else if (!f->s_check_pending) FG_CUDA(cudaMemsetAsync(f->d_sflag, f->s_binary ? 0 : 0xff, sizeof(int), st));
+	k_check_s_binary<<<wave_grid(n_cells, kThreads), kThreads, 0, st>>>(n_cells, f->s + first_cell, f->d_sflag);
 	f->lc.n++;
 	FG_CUDA(cudaGetLastError());
-	FG_CUDA(cudaMemcpyAsync(f->h_sflag, f->d_sflag, sizeof(int), cudaMemcpyDeviceToHost, f->st));
-	FG_CUDA(cudaEventRecord(f->ev_scheck, f->st));
+	k_word_to_host<<<1, 32, 0, st>>>(f->d_sflag, (volatile int*)f->h_sflag);
+	FG_CUDA(cudaEventRecord(f->ev_scheck, st));
 	f->s_check_pending = true;
 	return FLIPGPU_OK;
 }
@@ -1325,11 +1354,19 @@ int solve(FlipSim* f, int iters, float cp, float omega, bool drift, int order) {
 	return FLIPGPU_OK;
 }
 
-int g2p(FlipSim* f, float flip_ratio) {
+int g2p(FlipSim* f, float flip_ratio, bool stage = false) {
 	Geo g = geo(f);
 	if (g.np == 0) return FLIPGPU_OK;
 	int c = f->cur;
-	k_g2p<<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio);
+	if (stage && !f->identity) {
+		int b = 0;
+		FG_TRY(next_staging(f, &b));
+		k_g2p<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio, f->orig[c], f->staging[b]);
+		f->lc.n++;
+		FG_CUDA(cudaGetLastError());
+		return staged(f, b);
+	}
+	k_g2p<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio, nullptr, nullptr);
 	f->lc.n++;
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
@@ -1346,7 +1383,7 @@ int shard_rest_latch(FlipSim* f) {
 	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(pair, pair, 2, ncclFloat, ncclSum, f->comm, f->st));
 	k_rest_from_pair<<<1, 32, 0, f->st>>>(pair, f->d_rest);
 	f->lc.n += 3;
-	FG_CUDA(cudaMemcpyAsync(f->h_pinned, f->d_rest, sizeof(float), cudaMemcpyDeviceToHost, f->st));
+	k_word_to_host<<<1, 32, 0, f->st>>>((const int*)f->d_rest, (volatile int*)f->h_pinned);
 	return FLIPGPU_OK;
 }
 
@@ -1611,8 +1648,9 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	d.num_particles = 0;
 	FG_CUDA(cudaStreamCreateWithFlags(&f->st, cudaStreamNonBlocking));
 	FG_CUDA(cudaStreamCreateWithFlags(&f->st_copy, cudaStreamNonBlocking));
-	FG_CUDA(cudaStreamCreateWithFlags(&f->st_scatter, cudaStreamNonBlocking));
-	FG_CUDA(cudaEventCreateWithFlags(&f->ev_pos_final, cudaEventDisableTiming));
+	FG_CUDA(cudaStreamCreateWithFlags(&f->st_up, cudaStreamNonBlocking));
+	FG_CUDA(cudaEventCreateWithFlags(&f->ev_fence, cudaEventDisableTiming));
+	FG_CUDA(cudaEventCreateWithFlags(&f->ev_uploaded, cudaEventDisableTiming));
 	for (int b = 0; b < 2; b++) {
 		FG_CUDA(cudaEventCreateWithFlags(&f->ev_staged[b], cudaEventDisableTiming));
 		FG_CUDA(cudaEventCreateWithFlags(&f->ev_copied[b], cudaEventDisableTiming));
@@ -1676,9 +1714,10 @@ int flip_destroy(FlipSim* f) {
 	cudaFree(f->d_sflag);
 	if (f->h_sflag) cudaFreeHost(f->h_sflag);
 	if (f->ev_scheck) cudaEventDestroy(f->ev_scheck);
-	if (f->st_scatter) { cudaStreamSynchronize(f->st_scatter); cudaStreamDestroy(f->st_scatter); }
 	if (f->st_copy) { cudaStreamSynchronize(f->st_copy); cudaStreamDestroy(f->st_copy); }
-	if (f->ev_pos_final) cudaEventDestroy(f->ev_pos_final);
+	if (f->st_up) { cudaStreamSynchronize(f->st_up); cudaStreamDestroy(f->st_up); }
+	if (f->ev_fence) cudaEventDestroy(f->ev_fence);
+	if (f->ev_uploaded) cudaEventDestroy(f->ev_uploaded);
 	for (int b = 0; b < 2; b++) {
 		if (f->ev_staged[b]) cudaEventDestroy(f->ev_staged[b]);
 		if (f->ev_copied[b]) cudaEventDestroy(f->ev_copied[b]);
@@ -1729,9 +1768,20 @@ static int upload_impl(FlipSim* f, int field, const void* host, size_t count, bo
 				return FLIPGPU_EINVAL;
 		}
 	}
+	if (!wait && !f->sharded && (field == FLIP_S || field == FLIP_U || field == FLIP_V)) {
+		// per-frame caller writes: on the upload stream, behind the readers of the old values (everything queued so far)
+		FG_CUDA(cudaEventRecord(f->ev_fence, f->st));
+		FG_CUDA(cudaStreamWaitEvent(f->st_up, f->ev_fence, 0));
+		if (count) FG_CUDA(cudaMemcpyAsync(dst, host, count * 4, cudaMemcpyHostToDevice, f->st_up));
+		if (field == FLIP_S) FG_TRY(queue_s_check(f, 0, count, true, f->st_up));
+		FG_CUDA(cudaEventRecord(f->ev_uploaded, f->st_up));
+		f->upload_pending = true;
+		return FLIPGPU_OK;
+	}
+	FG_TRY(join_uploads(f));
 	if (count) FG_CUDA(cudaMemcpyAsync(dst, host, count * 4, cudaMemcpyHostToDevice, f->st));
 	// the blocked solvers pack s into one bit per neighbour; whether that is exact is checked on the device, behind the copy
-	if (field == FLIP_S) FG_TRY(queue_s_check(f, 0, count, true));
+	if (field == FLIP_S) FG_TRY(queue_s_check(f, 0, count, true, f->st));
 	if (wait) FG_CUDA(cudaStreamSynchronize(f->st));
 	return FLIPGPU_OK;
 }
@@ -1749,6 +1799,7 @@ int flip_readback(FlipSim* f, int field, void* host, size_t count) {
 	FG_CHECK(count == want, FLIPGPU_EINVAL, "flip_readback: field %d holds %zu elements, asked for %zu", field, want, count);
 	const void* srcp = grid_field_ptr(f, field);
 	FG_CHECK(srcp || !f->sharded, FLIPGPU_ESTATE, "sharded simulation: use flip_readback_particles / flip_readback_rows");
+	FG_TRY(join_uploads(f));
 	int np = f->d.num_particles, c = f->cur, n = 1 - c;
 	unsigned gr = pgrid(f);
 	if (!srcp) {
@@ -1816,6 +1867,7 @@ int flip_set_obstacle(FlipSim* f, float x, float y, float vx, float vy, float ra
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	DeviceGuard guard(f->device);
 	Geo g = geo(f);
+	FG_TRY(join_uploads(f));
 	if (g.nx > 3 && g.ny > 3) {
 		dim3 block(32, 8), grid(cdiv(g.nx - 3, 32), cdiv(g.ny - 3, 8));
 		k_set_obstacle<<<grid, block, 0, f->st>>>(g, x, y, vx, vy, radius, f->s, f->u, f->v);
@@ -1844,14 +1896,12 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0));
 		phase_mark(f, FLIP_PH_COLLIDE_MARK);
 		FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
-		// the positions of this step are final: in frame mode their caller-order copy is made now, beside P2G / solve / G2P
-		if (f->frame_mode && k == n_steps - 1) FG_TRY(stage_positions(f));
 		phase_mark(f, FLIP_PH_P2G);
 		FG_TRY(p2g(f));
 		phase_mark(f, FLIP_PH_SOLVE);
 		FG_TRY(solve(f, sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0, sp->solver_order));
 		phase_mark(f, FLIP_PH_G2P);
-		FG_TRY(g2p(f, sp->flip_ratio));
+		FG_TRY(g2p(f, sp->flip_ratio, f->frame_mode && k == n_steps - 1));   // frame mode: + the caller-order copy of the positions
 		phase_mark(f, FLIP_PH_COLORS);
 		if (sp->update_colors) FG_TRY(colors(f));
 		phase_mark(f, FLIP_PH_COUNT);
@@ -1966,11 +2016,12 @@ static int rows_copy(FlipSim* f, int field, void* host, int j_start, int n_rows,
 	FG_CHECK(base, FLIPGPU_EINVAL, "rows access is for grid fields (got %d)", field);
 	FG_CHECK(j_start >= 0 && n_rows >= 0 && j_start + n_rows <= f->d.f_num_y, FLIPGPU_EINVAL, "rows [%d,%d) outside the grid", j_start, j_start + n_rows);
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	size_t off = (size_t)j_start * f->d.f_num_x * 4, bytes = (size_t)n_rows * f->d.f_num_x * 4;
 	if (bytes) {
 		if (to_device) FG_CUDA(cudaMemcpyAsync(base + off, host, bytes, cudaMemcpyHostToDevice, f->st));
 		else FG_CUDA(cudaMemcpyAsync(host, base + off, bytes, cudaMemcpyDeviceToHost, f->st));
-		if (to_device && field == FLIP_S) FG_TRY(queue_s_check(f, (size_t)j_start * f->d.f_num_x, (size_t)n_rows * f->d.f_num_x, false));
+		if (to_device && field == FLIP_S) FG_TRY(queue_s_check(f, (size_t)j_start * f->d.f_num_x, (size_t)n_rows * f->d.f_num_x, false, f->st));
 	}
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	if (!to_device) FG_TRY(sor_workspace_check(f->ws));
@@ -1983,18 +2034,21 @@ int flip_phase_integrate(FlipSim* f, float dt, float gravity) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	return integrate_and_bin(f, true, false, dt, gravity);
 }
 int flip_phase_bin(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	return integrate_and_bin(f, false, true, 0.f, 0.f);
 }
 int flip_phase_separate(FlipSim* f, int num_iters, int update_colors) {
 	FG_CHECK(f && num_iters >= 0, FLIPGPU_EINVAL, "flip_phase_separate: bad argument");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	if (!f->bins_valid) FG_TRY(integrate_and_bin(f, false, true, 0.f, 0.f));
 	return separate(f, num_iters, update_colors != 0);
 }
@@ -2002,12 +2056,14 @@ int flip_phase_collide(FlipSim* f, float ox, float oy, float ovx, float ovy, flo
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	return collide_mark(f, true, false, ox, oy, ovx, ovy, orad);
 }
 int flip_phase_p2g(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
 	FG_TRY(collide_mark(f, false, true, 0, 0, 0, 0, 0));
 	return p2g(f);
@@ -2016,6 +2072,7 @@ int flip_phase_solve(FlipSim* f, int iters, float dt, float omega, int drift, in
 	FG_CHECK(f && dt > 0 && iters >= 0, FLIPGPU_EINVAL, "flip_phase_solve: bad argument");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	// :452-454
 	FG_CUDA(cudaMemsetAsync(f->p, 0, (size_t)f->d.f_num_cells * 4, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->prev_u, f->u, (size_t)f->d.f_num_cells * 4, cudaMemcpyDeviceToDevice, f->st));
@@ -2026,12 +2083,14 @@ int flip_phase_g2p(FlipSim* f, float flip_ratio) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	return g2p(f, flip_ratio);
 }
 int flip_phase_colors(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	FG_CHECK(!f->sharded, FLIPGPU_ESTATE, "flip_phase_* are single-GPU replay entry points (a sharded step needs its exchanges: flip_step)");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	return colors(f);
 }
 
@@ -2047,6 +2106,7 @@ int flip_get_scalar(FlipSim* f, int which, float* out) {
 		case FLIP_SCALAR_RESIDUAL_MAX:
 		case FLIP_SCALAR_RESIDUAL_RMS: {
 			float r2[2];
+			FG_TRY(join_uploads(f));
 			FG_TRY(sor_residual(sor_view(f), true, f->d_partials, kPartials, r2, f->st, &f->lc));
 			*out = which == FLIP_SCALAR_RESIDUAL_MAX ? r2[0] : r2[1];
 			return FLIPGPU_OK;
@@ -2085,6 +2145,7 @@ int flip_get_exact_order_info(FlipSim* f, int* levels, int* drifted) {
 int flip_synchronize(FlipSim* f) {
 	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
 	DeviceGuard guard(f->device);
+	FG_TRY(join_uploads(f));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	return sor_workspace_check(f->ws);  // FLIPGPU_ESTATE if a solver dependency wait timed out since the last check
 }

@@ -75,6 +75,7 @@ struct SysArgs {
 	int* counter;
 	int* prog;           // [nq][nw] rows complete
 	int* status;
+	volatile int* host_status;   // pinned host mirror of the error word, written by the kernel on a time-out
 	float* ring;         // [nw][2][ns][RSF]
 	float cp, omega;
 	unsigned long long* prof;  // optional (FLIPGPU_SOR_PROFILE): cycles in [0] dependency waits [1] flush+publish [2] land+fetch [3] steps, [4] tasks, [5] task cycles
@@ -217,7 +218,7 @@ __device__ __forceinline__ void sys_exchange(SysState<K, DRIFT>& s, const float 
 // error word).  No fence on this side: every datum the producer published is read with ld.cg (L2) AFTER the poll -- the
 // loads are issued behind the branch that consumes the polled value -- and the producer's release orders its stores before
 // the progress word.
-__device__ __forceinline__ int sys_wait(const int* pr, int need, int* status, int lane) {
+__device__ __forceinline__ int sys_wait(const int* pr, int need, int* status, volatile int* host_status, int lane) {
 	int seen = 0;
 	if (lane == 0) {
 		long long spins = 0;
@@ -225,7 +226,7 @@ __device__ __forceinline__ int sys_wait(const int* pr, int need, int* status, in
 			if (++spins > (1ll << 24) || ((spins & 255) == 0 && *((volatile const int*)status) != 0)) { seen = -1; break; }
 			__nanosleep(20);
 		}
-		if (seen < 0) atomicExch(status, FLIPGPU_ESTATE);
+		if (seen < 0) { atomicExch(status, FLIPGPU_ESTATE); *host_status = FLIPGPU_ESTATE; }
 	}
 	return __shfl_sync(kFull, seen, 0);
 }
@@ -323,8 +324,8 @@ __global__ void __launch_bounds__(32 * kSysWarps, 1) sor_systolic_kernel(SysArgs
 			need = min(need, ns);
 			if (have_left >= need && have_prev >= need) return;
 			const long long c0 = clock64();
-			if (have_left < need) { have_left = sys_wait(dep_left, need, A.status, lane); alive = have_left >= 0; }
-			if (alive && have_prev < need) { have_prev = sys_wait(dep_prev, need, A.status, lane); alive = have_prev >= 0; }
+			if (have_left < need) { have_left = sys_wait(dep_left, need, A.status, A.host_status, lane); alive = have_left >= 0; }
+			if (alive && have_prev < need) { have_prev = sys_wait(dep_prev, need, A.status, A.host_status, lane); alive = have_prev >= 0; }
 			c_wait += clock64() - c0;
 		};
 
@@ -519,7 +520,7 @@ static int sys_launch(SysWorkspace* w, const SorGrid& g, int chunks, float cp, f
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
 	SysArgs A;
 	A.nf = g.nf; A.ns = g.ns; A.nw = nw; A.nq = chunks; A.vf = g.vel_f; A.vs = g.vel_s; A.p = g.p; A.cd = w->cd; A.tasks = w->tasks;
-	A.n_tasks = n_tasks; A.counter = w->counter; A.prog = w->prog; A.status = w->status; A.ring = w->ring; A.cp = cp; A.omega = omega; A.prof = w->prof;
+	A.n_tasks = n_tasks; A.counter = w->counter; A.prog = w->prog; A.status = w->status; A.host_status = w->h_status; A.ring = w->ring; A.cp = cp; A.omega = omega; A.prof = w->prof;
 	const void* fn = g.x_fast ? (use_drift ? (const void*)sor_systolic_kernel<K, true, true> : (const void*)sor_systolic_kernel<K, true, false>)
 	                          : (use_drift ? (const void*)sor_systolic_kernel<K, false, true> : (const void*)sor_systolic_kernel<K, false, false>);
 	const size_t smem = (size_t)kSysWarps * L::kWarpFloats * 4;
@@ -577,8 +578,7 @@ int sor_solve_systolic(SysWorkspace** wsp, const SorGrid& g, int iters, float cp
 			default: FG_TRY(sys_launch<1>(w, g, chunks, cp, omega, use_drift, st, lc)); break;
 		}
 	}
-	FG_CUDA(cudaMemcpyAsync(w->h_status, w->status, 4, cudaMemcpyDeviceToHost, st));
-	return FLIPGPU_OK;
+		return FLIPGPU_OK;
 }
 
 }  // namespace fg

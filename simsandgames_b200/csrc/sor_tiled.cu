@@ -47,7 +47,8 @@ struct TiledArgs {
 	int epoch;
 	float cp, omega;
 	unsigned long long* prof;  // [0] wait [1] load [2] compute [3] write-back cycles (thread 0 of every CTA), [4] tiles
-	int* status;               // device error word: a dependency wait that timed out stores FLIPGPU_ESTATE here
+	int* status;               // device error word: a dependency wait that timed out stores FLIPGPU_ESTATE here ...
+	volatile int* host_status; // ... and in this word of pinned host memory (written by the kernel: no D2H copy on the stream)
 };
 
 // ceil(2^16 / d): floor(n / d) == (n * magic[d]) >> 16 for every n < 1024, d <= 32 (checked exhaustively)
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 				if (v1 == A.epoch && v2 == A.epoch && v3 == A.epoch) { ok = 1; break; }
 				if ((spins & 1023) == 1023 && *((volatile const int*)A.status) != 0) break;  // another CTA already gave up
 			}
-			if (!ok) atomicExch(A.status, FLIPGPU_ESTATE);
+			if (!ok) { atomicExch(A.status, FLIPGPU_ESTATE); *A.host_status = FLIPGPU_ESTATE; }
 			s_ok = ok;
 			__threadfence();
 		}
@@ -279,7 +280,7 @@ struct SorWorkspace {
 	SysWorkspace* sys = nullptr;  // workspace of the register-systolic kernel (sor_systolic.cu, FLIP_SOLVER_LEX_SYSTOLIC)
 	int sms = 0;
 	int* status = nullptr;    // device error word raised by a dependency wait that timed out ...
-	int* h_status = nullptr;  // ... mirrored into pinned host memory behind every solve launch
+	int* h_status = nullptr;  // ... and this word of pinned host memory, written by the kernel itself
 };
 
 // diagnostic: cycles spent per tile phase (enabled by FLIPGPU_SOR_PROFILE=1 in the environment at plan time)
@@ -390,7 +391,7 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;
 	A.kc = w->kc; A.flags = w->flags; A.counter = w->counter; A.epoch = w->epoch; A.cp = cp; A.omega = omega; A.prof = w->prof;
-	A.act = w->act; A.na = w->na; A.nb = w->nb; A.status = w->status;
+	A.act = w->act; A.na = w->na; A.nb = w->nb; A.status = w->status; A.host_status = w->h_status;
 	const int kw = w->kc <= 8 ? 8 : 16;  // warps per CTA: the box staging is unrolled for exactly this many threads
 	dim3 block(kTile, kw);
 	int per_sm = 0;
@@ -408,8 +409,7 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	int blocks = std::min(w->n_tiles, std::max(1, per_sm) * w->sms);
 	void* args[] = {&A};
 	FG_CUDA(cudaLaunchKernel(fn, dim3(blocks), block, args, tile_smem, st));
-	FG_CUDA(cudaMemcpyAsync(w->h_status, w->status, 4, cudaMemcpyDeviceToHost, st));
-	if (lc) lc->n += 2;
+		if (lc) lc->n += 2;
 	return FLIPGPU_OK;
 }
 
