@@ -727,13 +727,16 @@ __global__ void __launch_bounds__(kThreads) k_shard_vmax(int np, const float2* _
 	int mi = warp_max(__float_as_int(m));
 	if ((threadIdx.x & 31) == 0 && mi > 0) atomicMax(vmax_bits, mi);
 }
-// ghost band in rows: how far a particle can travel in one step (integration + a separation/collision allowance) plus the
-// reach of the bilinear stencil -- every particle that can touch this rank's rows during the step must be present
-__global__ void k_shard_band(const int* __restrict__ vmax_bits, float dt, float gravity, float h, int max_band, int* __restrict__ band) {
+// Ghost band in rows: every particle that can touch this rank's rows during the step must be present.  A particle moves at
+// most (vmax + |g| dt) dt by integration, then up to one overlap (2.2r hash cell + r push) per separation sweep -- each
+// Jacobi sweep also widens the dependency cone by one hash cell -- and its bilinear stencil reaches one more cell; +2 rows
+// of slack.  The same value on every rank (vmax is all-reduced); the host refuses a band wider than the thinnest slab.
+__global__ void k_shard_band(const int* __restrict__ vmax_bits, float dt, float gravity, float h, float r, int sep_iters, int* __restrict__ band) {
 	if (threadIdx.x != 0) return;
 	float v = __int_as_float(*vmax_bits) + fabsf(gravity) * dt;
-	int b = (int)ceilf(v * dt / h) + 4;
-	*band = min(max(b, 6), max_band);
+	float reach = v * dt / h + (float)sep_iters * (3.2f * r) / h;
+	int b = (int)ceilf(reach) + 1 + 2;
+	*band = max(b, 6);
 }
 
 // Step-start bookkeeping.  Ownership is by position: a rank owns the particles whose cell row lies in its slab.  Out of
@@ -745,25 +748,55 @@ __global__ void __launch_bounds__(kThreads) k_shard_classify(Geo g, int j0, int 
                                                              const float2* __restrict__ pos, const float2* __restrict__ vel,
                                                              const int* __restrict__ id, ShardPack keep, ShardPack down, ShardPack up,
                                                              int* __restrict__ counters /* [0] keep [1] down [2] up */, int cap_send, int exchange) {
+	// Slots are claimed per CTA: one atomic per counter and block instead of one per warp (64 M particles -> 2 M same-address
+	// atomics serialise at the L2: 2.9 ms per step at S2 before this, profiles/r2_sharded.md).  Any order of the kept particles
+	// will do: the counting sort that follows orders by (hash cell, global id).
 	const int band = exchange ? *band_p : 0;
-	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
-		float2 p = pos[t];
-		int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
-		if (row < j0 || row >= j1) continue;
-		float2 v = vel[t];
-		int gid = id[t];
-		int k = atomicAdd(counters + 0, 1);
-		keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
-		if (!exchange) continue;
-		if (has_down && row < j0 + band) {
-			int m = atomicAdd(counters + 1, 1);
-			if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = gid; }
+	__shared__ int s_cnt[3], s_base[3];
+	const int lane = threadIdx.x & 31;
+	for (int t0 = blockIdx.x * blockDim.x; t0 < g.np; t0 += gridDim.x * blockDim.x) {
+		const int t = t0 + threadIdx.x;
+		if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		float2 p = make_float2(0.f, 0.f), v = make_float2(0.f, 0.f);
+		int gid = 0;
+		bool own = false, go_down = false, go_up = false;
+		if (t < g.np) {
+			p = pos[t];
+			const int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
+			own = row >= j0 && row < j1;
+			if (own) {
+				v = vel[t]; gid = id[t];
+				go_down = exchange && has_down && row < j0 + band;
+				go_up = exchange && has_up && row >= j1 - band;
+			}
 		}
-		if (has_up && row >= j1 - band) {
-			int m = atomicAdd(counters + 2, 1);
-			if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = gid; }
+		// warp-level ranks, then one shared-memory add per warp and class
+		int slot[3];
+		const bool flag[3] = {own, go_down, go_up};
+#pragma unroll
+		for (int c = 0; c < 3; c++) {
+			const unsigned m = __ballot_sync(0xffffffffu, flag[c]);
+			int base = 0;
+			if (lane == 0 && m) base = atomicAdd(&s_cnt[c], __popc(m));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			slot[c] = base + __popc(m & ((1u << lane) - 1u));
 		}
+		__syncthreads();
+		if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]) : 0;
+		__syncthreads();
+		if (own) { const int k = s_base[0] + slot[0]; keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid; }
+		if (go_down) { const int m = s_base[1] + slot[1]; if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = gid; } }
+		if (go_up) { const int m = s_base[2] + slot[2]; if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = gid; } }
+		__syncthreads();
 	}
+}
+
+// capacity check of the exchange, on the device: [7] = 1 if this rank cannot send or hold what the step needs.  The flag is
+// all-reduced (max) before the host looks at it, so every rank takes the error exit together and none stays blocked in NCCL.
+__global__ void k_shard_check(int* __restrict__ c, int cap_send, int max_particles) {
+	if (threadIdx.x != 0) return;
+	c[7] = (c[1] > cap_send || c[2] > cap_send || (long long)c[0] + c[3] + c[4] > (long long)max_particles) ? 1 : 0;
 }
 
 // rest-density latch across slabs: per-rank (sum, count) over own rows, summed over ranks (flip_fluid.h:321-332)
@@ -968,7 +1001,7 @@ struct FlipSim {
 	SorWorkspace* ws = nullptr;
 	// slab sharding (flip_create_sharded): rank owns grid rows [j0, j1); arrays keep the global size, only the window is processed
 	bool sharded = false;
-	int rank = 0, nranks = 1, j0 = 0, j1 = 0, halo = 9, band = 6;
+	int rank = 0, nranks = 1, j0 = 0, j1 = 0, halo = 9, band = 6, min_slab_rows = 0;
 	int gy0 = 0, gy1 = 0, hy0 = 0, hy1 = 0;
 	ncclComm_t comm = nullptr;
 	float2 *send_pos[2] = {nullptr, nullptr}, *send_vel[2] = {nullptr, nullptr};
@@ -1411,7 +1444,7 @@ int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows)
 }
 
 // keep what this rank owns (by position), refresh the ghosts from both neighbours
-int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
+int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters) {
 	Geo g = geo(f);
 	const int c = f->cur, n = 1 - c;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
@@ -1419,7 +1452,7 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 	// ghost band for this step from the fastest owned particle anywhere (device-side: no host round trip)
 	if (g.np > 0) { k_shard_vmax<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->vel[c], f->d_counters + 5); f->lc.n++; }
 	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 5, f->d_counters + 5, 1, ncclInt, ncclMax, f->comm, f->st));
-	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 5, dt, gravity, f->d.h, std::max(f->j1 - f->j0 - 1, 6), f->d_counters + 6);
+	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 5, dt, gravity, f->d.h, f->d.particle_radius, sep_iters, f->d_counters + 6);
 	f->lc.n++;
 	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
 	if (g.np > 0) {
@@ -1440,10 +1473,20 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity) {
 		}
 		FG_NCCL(g_nccl.GroupEnd());
 	}
+	k_shard_check<<<1, 32, 0, f->st>>>(f->d_counters, f->cap_send, f->d.max_particles);
+	f->lc.n++;
+	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 7, f->d_counters + 7, 1, ncclInt, ncclMax, f->comm, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	const int n_keep = f->h_counters[0], n_down = f->h_counters[1], n_up = f->h_counters[2], from_down = f->h_counters[3], from_up = f->h_counters[4];
+	FG_CHECK(f->h_counters[7] == 0, FLIPGPU_ESTATE, "shard: a rank ran out of room in this step's particle exchange (here: %d owned + %d + %d received of %d slots, "
+	         "%d / %d boundary particles of %d send slots) -- every rank stops", n_keep, from_down, from_up, f->d.max_particles, n_down, n_up, f->cap_send);
 	f->band = f->h_counters[6];
+	// (the band is the same number on every rank and min_slab_rows is too: all ranks take this exit together, none is left
+	// blocked in the NCCL group below)
+	FG_CHECK(f->nranks == 1 || f->band <= f->min_slab_rows - 1, FLIPGPU_ESTATE,
+	         "shard: the ghost band (%d rows: fastest particle, %d separation sweeps) is wider than the thinnest slab (%d rows) -- use fewer ranks or a smaller dt",
+	         f->band, sep_iters, f->min_slab_rows);
 	FG_CHECK(n_down <= f->cap_send && n_up <= f->cap_send, FLIPGPU_ESTATE, "shard: %d/%d boundary particles exceed the send capacity %d", n_down, n_up, f->cap_send);
 	FG_CHECK((long long)n_keep + from_down + from_up <= f->d.max_particles, FLIPGPU_ESTATE, "shard: %d owned + %d + %d received exceed max_particles %d",
 	         n_keep, from_down, from_up, f->d.max_particles);
@@ -1524,7 +1567,7 @@ int shard_step(FlipSim* f, const FlipStepParams* sp) {
 	// integrate_bin, post-P2G halo rows under p2g, post-solve halo rows under g2p
 	if (f->timings_on) collect_slot(f, f->ev_slot);
 	phase_mark(f, FLIP_PH_INTEGRATE_BIN);
-	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity));              // migrants change owner, ghosts are refreshed
+	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity, sp->separate_particles ? sp->num_particle_iters : 0));              // migrants change owner, ghosts are refreshed
 	// (the exchange synchronised the stream, so the previous step -- and its copy of the rest density -- is complete on
 	// every rank: all ranks take the same branch below and issue the same NCCL calls)
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
@@ -1925,6 +1968,7 @@ int flip_create_sharded(const FlipParams* pr, int global_particles, int rank, in
 	f->sharded = true; f->rank = rank; f->nranks = nranks;
 	f->j0 = (int)((long long)ny * rank / nranks);
 	f->j1 = (int)((long long)ny * (rank + 1) / nranks);
+	f->min_slab_rows = ny / nranks;
 	if (nranks > 1 && f->j1 - f->j0 < f->halo + 1) {
 		flip_destroy(f);
 		fg::set_error("flip_create_sharded: %d rows over %d ranks leaves slabs thinner than the %d-row halo", ny, nranks, f->halo);

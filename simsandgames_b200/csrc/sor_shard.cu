@@ -237,12 +237,11 @@ int sorshard_solve(SorShard* h, int iters, float cp, float omega, int drift, flo
 		h->exchanges++;
 		return FLIPGPU_OK;
 	};
-	// OPT-IN (FLIPGPU_SHARD_TILED=1, not yet validated on hardware): one launch of the temporally blocked red-black
-	// kernel per exchange -- its 8 colour passes are exactly what the 9-row halo allows -- as the sharded FLIP step
-	// already does (flip.cu shard_solve).  Rows of the local window that are the global border, or outside the grid,
-	// are deactivated; output = own rows +- 1 (completes the face rows two slabs share).
-	const char* tiled_env = getenv("FLIPGPU_SHARD_TILED");
-	if (tiled_env && atoi(tiled_env) != 0 && h->nranks > 1 && h->s_binary && K == sor_rb_passes_per_round()) {
+	// With 0/1-valued s: ONE launch of the temporally blocked red-black kernel per exchange -- its 8 colour passes are exactly
+	// what the 9-row halo allows -- as the sharded FLIP step does (flip.cu shard_solve; bit-identical to one launch per
+	// colour pass, validated on 2 GPUs: tests/test_gpu_multi.py).  Rows of the local window that are the global border, or
+	// outside the grid, are deactivated; output = own rows +- 1 (completes the face rows two slabs share).
+	if (h->nranks > 1 && h->s_binary && K == sor_rb_passes_per_round()) {
 		const size_t n = (size_t)h->nf * h->rows;
 		if (!h->alt_f) {
 			float** alts[] = {&h->alt_f, &h->alt_s, &h->alt_p};
