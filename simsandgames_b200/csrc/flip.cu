@@ -326,6 +326,43 @@ __global__ void k_init_colors(int n, float* c) {  // flip_fluid.h:94-96
 	}
 }
 
+// ------------------------------------------------------------------ F4 / F5 per-particle pieces (used by k_collide_mark and the fused last separation sweep)
+struct CollideArgs {
+	float ox, oy, ovx, ovy, md2;          // obstacle centre, velocity, (r + orad)^2
+	float min_x, max_x, min_y, max_y;     // tank walls for particle centres, flip_fluid.h:256-259
+};
+__device__ __forceinline__ CollideArgs collide_args(const Geo& g, float ox, float oy, float ovx, float ovy, float orad) {
+	CollideArgs a;
+	const float md = g.r + orad;
+	a.ox = ox; a.oy = oy; a.ovx = ovx; a.ovy = ovy; a.md2 = md * md;
+	a.min_x = g.h + g.r; a.max_x = g.h * (float)(g.nx - 1) - g.r;
+	a.min_y = g.h + g.r; a.max_y = g.h * (float)(g.ny - 1) - g.r;
+	return a;
+}
+// handleParticleCollisions for one particle (flip_fluid.h:262-288); returns true if the velocity changed
+__device__ __forceinline__ bool collide_one(const CollideArgs& a, float2& p, float2& v) {
+	bool hit = false;
+	float dx = p.x - a.ox, dy = p.y - a.oy;
+	if (dx * dx + dy * dy < a.md2) { v.x = a.ovx; v.y = a.ovy; hit = true; }  // Q12: velocity only, no push-out
+	if (p.x < a.min_x) { p.x = a.min_x; v.x = 0.f; hit = true; }
+	if (p.x > a.max_x) { p.x = a.max_x; v.x = 0.f; hit = true; }
+	if (p.y < a.min_y) { p.y = a.min_y; v.y = 0.f; hit = true; }
+	if (p.y > a.max_y) { p.y = a.max_y; v.y = 0.f; hit = true; }
+	return hit;
+}
+// fluid-cell marking (flip_fluid.h:352-359) + key and histogram of the index-only sort by stencil base cell (:301-308)
+__device__ __forceinline__ void mark_one(const Geo& g, float2 p, int t, int* __restrict__ cell_type, int* __restrict__ gkeys, int* __restrict__ gcount) {
+	int xi = clampi((int)(g.inv_h * p.x), 0, g.nx - 1);
+	int yi = clampi((int)(g.inv_h * p.y), g.gy0, g.gy1 - 1);
+	int c = xi + g.nx * yi;
+	if (cell_type[c] == AIR_CELL) cell_type[c] = FLUID_CELL;  // all racing writers store the same value
+	float x = clampf(p.x, g.h, g.xmax_c), y = clampf(p.y, g.h, g.ymax_c);
+	int x0 = clampi((int)(g.inv_h * (x - g.h2)), 0, g.nx - 1), y0 = clampi((int)(g.inv_h * (y - g.h2)), g.gy0, g.gy1 - 1);
+	int key = x0 + g.nx * y0;
+	gkeys[t] = key;
+	atomicAdd(gcount + key, 1);  // integer histogram: order-independent
+}
+
 // ------------------------------------------------------------------ F3: separation sweep (flip_fluid.h:201-250)
 // The reference sweep is a serial Gauss-Seidel over particles in caller order with an asymmetric pair
 // update (Q1); no parallel schedule reproduces it.  This is the deterministic parallel schedule: one
@@ -334,10 +371,16 @@ __global__ void k_init_colors(int n, float* c) {  // flip_fluid.h:94-96
 // CURRENT position as :208-213, bins from before the first sweep as Q6).  Neighbours are visited
 // row by row in slot order; oracle/flip_oracle.c:orcflip_separate_jacobi is the same schedule on the CPU
 // and this kernel is bit-exact against it.  Statistical distance to the serial sweep: tests T3.
-template <bool COLORS>
+// FUSE: the last sweep of a step also runs the collision pass, the fluid-cell marking and the key / histogram of the P2G
+// lists on the position it has just computed (the same device functions as k_collide_mark: identical results), so the
+// positions cross HBM once instead of three times and the velocity is only written where a wall or the obstacle changed it.
+template <bool COLORS, bool FUSE>
 __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
                                                        float2* __restrict__ pos_out, const float* __restrict__ col_in,
-                                                       float* __restrict__ col_out) {
+                                                       float* __restrict__ col_out, float2* __restrict__ vel, float ox, float oy,
+                                                       float ovx, float ovy, float orad, int* __restrict__ cell_type,
+                                                       int* __restrict__ gkeys, int* __restrict__ gcount) {
+	const CollideArgs ca = collide_args(g, ox, oy, ovx, ovy, orad);
 	const float min_dist = 2.f * g.r;
 	const float min_dist_sq = min_dist * min_dist;
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
@@ -392,7 +435,13 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 				}
 			}
 		}
-		pos_out[t] = make_float2(ax, ay);
+		float2 pn = make_float2(ax, ay);
+		if (FUSE) {
+			float2 v = vel[t];
+			if (collide_one(ca, pn, v)) vel[t] = v;
+			mark_one(g, pn, t, cell_type, gkeys, gcount);
+		}
+		pos_out[t] = pn;
 		if (COLORS) { col_out[3 * (size_t)t] = c0; col_out[3 * (size_t)t + 1] = c1; col_out[3 * (size_t)t + 2] = c2; }
 	}
 }
@@ -430,34 +479,16 @@ __global__ void __launch_bounds__(kThreads) k_collide_mark(Geo g, float2* __rest
                                                            float oy, float ovx, float ovy, float orad,
                                                            int* __restrict__ cell_type, int* __restrict__ gkeys,
                                                            int* __restrict__ gcount) {
-	const float md = g.r + orad, md2 = md * md;
-	const float min_x = g.h + g.r, max_x = g.h * (float)(g.nx - 1) - g.r;
-	const float min_y = g.h + g.r, max_y = g.h * (float)(g.ny - 1) - g.r;
+	const CollideArgs ca = collide_args(g, ox, oy, ovx, ovy, orad);
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
 		float2 p = pos[t];
 		if (COLLIDE) {
 			float2 v = vel[t];
-			float dx = p.x - ox, dy = p.y - oy;
-			if (dx * dx + dy * dy < md2) { v.x = ovx; v.y = ovy; }  // Q12: velocity only, no push-out
-			if (p.x < min_x) { p.x = min_x; v.x = 0.f; }
-			if (p.x > max_x) { p.x = max_x; v.x = 0.f; }
-			if (p.y < min_y) { p.y = min_y; v.y = 0.f; }
-			if (p.y > max_y) { p.y = max_y; v.y = 0.f; }
+			collide_one(ca, p, v);
 			pos[t] = p;
 			vel[t] = v;
 		}
-		if (cell_type) {
-			int xi = clampi((int)(g.inv_h * p.x), 0, g.nx - 1);
-			int yi = clampi((int)(g.inv_h * p.y), g.gy0, g.gy1 - 1);
-			int c = xi + g.nx * yi;
-			if (cell_type[c] == AIR_CELL) cell_type[c] = FLUID_CELL;  // all racing writers store the same value
-			// base cell of the stencil, exactly as :301-308 (clamped position, cell-centred offset)
-			float x = clampf(p.x, g.h, g.xmax_c), y = clampf(p.y, g.h, g.ymax_c);
-			int x0 = clampi((int)(g.inv_h * (x - g.h2)), 0, g.nx - 1), y0 = clampi((int)(g.inv_h * (y - g.h2)), g.gy0, g.gy1 - 1);
-			int key = x0 + g.nx * y0;
-			gkeys[t] = key;
-			atomicAdd(gcount + key, 1);  // integer histogram: order-independent
-		}
+		if (cell_type) mark_one(g, p, t, cell_type, gkeys, gcount);
 	}
 }
 
@@ -1243,12 +1274,18 @@ int separate_exact(FlipSim* f, int iters, bool colors) {
 	return FLIPGPU_OK;
 }
 
-int separate(FlipSim* f, int iters, bool colors) {
+struct FuseCollide {   // obstacle of the collision pass that the last separation sweep runs itself (flip_step fast path)
+	float ox, oy, ovx, ovy, orad;
+};
+int mark_prepare(FlipSim* f);
+
+int separate(FlipSim* f, int iters, bool colors, const FuseCollide* fuse = nullptr) {
 	Geo g = geo(f);
 	if (g.np == 0) return FLIPGPU_OK;
 	FG_TRY(positions_will_change(f));
 	if (f->exact_order) return separate_exact(f, iters, colors);
 	if (colors) FG_TRY(ensure_colors(f));
+	if (fuse) FG_TRY(mark_prepare(f));   // cell types from s and a cleared list histogram must exist before the fused sweep marks cells
 	// Sweeps ping-pong between the two position buffers; velocities (and ids) stay in buffer `cur`,
 	// so after an odd number of sweeps the result is copied back rather than swapping every array.
 	int c = f->cur;
@@ -1257,8 +1294,11 @@ int separate(FlipSim* f, int iters, bool colors) {
 	float* ca = colors ? f->col[c] : nullptr;
 	float* cb = colors ? f->col[1 - c] : nullptr;
 	for (int it = 0; it < iters; it++) {
-		if (colors) k_separate<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb);
-		else k_separate<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr);
+		if (fuse && it == iters - 1) {
+			if (colors) k_separate<true, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb, f->vel[c], fuse->ox, fuse->oy, fuse->ovx, fuse->ovy, fuse->orad, f->cell_type, f->keys, f->gcount);
+			else k_separate<false, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr, f->vel[c], fuse->ox, fuse->oy, fuse->ovx, fuse->ovy, fuse->orad, f->cell_type, f->keys, f->gcount);
+		} else if (colors) k_separate<true, false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, ca, cb, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr);
+		else k_separate<false, false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->first, a, b, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, nullptr);
 		f->lc.n++;
 		std::swap(a, b);
 		std::swap(ca, cb);
@@ -1271,18 +1311,27 @@ int separate(FlipSim* f, int iters, bool colors) {
 	return FLIPGPU_OK;
 }
 
-int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad) {
+// cell_type from s (flip_fluid.h:348-350) and an empty histogram for the P2G lists
+int mark_prepare(FlipSim* f) {
 	Geo g = geo(f);
 	FG_TRY(join_uploads(f));   // s (cell types), u, v (solid restore of the P2G) are read from here on
-	if (collide) FG_TRY(positions_will_change(f));
+	const size_t goff = (size_t)g.nx * g.gy0;
+	const int C = g.nx * (g.gy1 - g.gy0);
+	k_cell_type_from_s<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->s + goff, f->cell_type + goff);
+	f->lc.n++;
+	FG_CUDA(cudaMemsetAsync(f->gcount + goff, 0, (size_t)C * 4, f->st));
+	return FLIPGPU_OK;
+}
+
+// particles_done: the last separation sweep already ran the collision pass, the marking and the list histogram
+int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float ovx, float ovy, float orad, bool particles_done = false) {
+	Geo g = geo(f);
+	FG_TRY(join_uploads(f));
+	if (collide && !particles_done) FG_TRY(positions_will_change(f));
 	const size_t goff = (size_t)g.nx * g.gy0;
 	int c = f->cur, C = g.nx * (g.gy1 - g.gy0);
-	if (mark) {
-		k_cell_type_from_s<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->s + goff, f->cell_type + goff);
-		f->lc.n++;
-		FG_CUDA(cudaMemsetAsync(f->gcount + goff, 0, (size_t)C * 4, f->st));
-	}
-	if (g.np > 0) {
+	if (mark && !particles_done) FG_TRY(mark_prepare(f));
+	if (g.np > 0 && !particles_done) {
 		int* ct = mark ? f->cell_type : nullptr;
 		if (collide) k_collide_mark<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, f->keys, f->gcount);
 		else k_collide_mark<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], ox, oy, ovx, ovy, orad, ct, f->keys, f->gcount);
@@ -1936,9 +1985,12 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		phase_mark(f, FLIP_PH_INTEGRATE_BIN);
 		FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));
 		phase_mark(f, FLIP_PH_SEPARATE);
-		if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0));
+		// the last sweep runs the collision / marking pass itself (same device functions, identical results)
+		const bool fused = sp->separate_particles && sp->num_particle_iters >= 1 && !f->exact_order && f->d.num_particles > 0;
+		const FuseCollide fc{sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius};
+		if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0, fused ? &fc : nullptr));
 		phase_mark(f, FLIP_PH_COLLIDE_MARK);
-		FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
+		FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius, fused));
 		phase_mark(f, FLIP_PH_P2G);
 		FG_TRY(p2g(f));
 		phase_mark(f, FLIP_PH_SOLVE);
