@@ -195,6 +195,34 @@ int euler_synchronize(EulerSim* sim);
 int euler_get_stream(EulerSim* sim, void** stream);
 int euler_get_launch_count(EulerSim* sim, long long* launches);
 
+/* ------------------------------------------------------------------ 3D Eulerian smoke (fluid3d.h)
+ * struct Fluid3D, eulerian_fluid/src/fluid3d.h:19-368 (the 3D transcription of fluid.h; no reference target compiles it).
+ * Same state arrays and calls; x-fastest layout ix(i,j,k) = i + num_x*j + num_y*num_x*k (fluid3d.h:131-133) on the wire. */
+typedef struct Fluid3DSim Fluid3DSim;
+typedef enum {
+	FLUID3D_U = 0, FLUID3D_V, FLUID3D_W, FLUID3D_NEW_U, FLUID3D_NEW_V, FLUID3D_NEW_W, FLUID3D_PRESSURE, FLUID3D_M, FLUID3D_NEW_M, /* float[C] */
+	FLUID3D_SOLID,  /* unsigned char[C] (the reference's bool[]) */
+	FLUID3D_FIELD_COUNT
+} Fluid3DField;
+typedef struct { int num_x, num_y, num_z, num_cells; float density, h; } Fluid3DDims;
+
+int fluid3d_create(int x, int y, int z, float density, float h, int device, Fluid3DSim** out);  /* Fluid3D(x,y,z,d,h) fluid3d.h:40 */
+int fluid3d_destroy(Fluid3DSim* sim);
+int fluid3d_get_dims(Fluid3DSim* sim, Fluid3DDims* dims);
+int fluid3d_upload(Fluid3DSim* sim, int field, const void* host, size_t count);
+int fluid3d_readback(Fluid3DSim* sim, int field, void* host, size_t count);
+/* solveIncompressibility fluid3d.h:135-182; order: FLIP_SOLVER_LEX_WAVEFRONT (the reference's loop order as a plane wavefront,
+ * bit-identical) or FLIP_SOLVER_RED_BLACK (parity of i+j+k) */
+int fluid3d_project(Fluid3DSim* sim, int iters, float dt, int order);
+int fluid3d_extrapolate(Fluid3DSim* sim);                 /* fluid3d.h:185-211 */
+int fluid3d_advect_vel(Fluid3DSim* sim, float dt);        /* fluid3d.h:305-346, incl. its k < num_y loop bound (:311) */
+int fluid3d_advect_smoke(Fluid3DSim* sim, float dt);      /* fluid3d.h:348-367 */
+int fluid3d_step(Fluid3DSim* sim, int iters, float dt, int order, int n_steps);   /* project, extrapolate, advectVel, advectSmoke */
+/* sampleField fluid3d.h:213-264 at n query points (field: 0 U, 1 V, 2 W, 3 S) */
+int fluid3d_sample_field(Fluid3DSim* sim, int field, const float* xs, const float* ys, const float* zs, float* out, size_t n);
+int fluid3d_synchronize(Fluid3DSim* sim);
+int fluid3d_get_launch_count(Fluid3DSim* sim, long long* launches);
+
 /* ------------------------------------------------------------------ multi-GPU: slab-sharded FLIP step
  * One process per GPU.  The grid is cut into nranks slabs of rows (y); rank r owns rows [j0,j1) and the particles
  * whose cell lies in them (ownership by position; global_particles = the number of caller indices in use).

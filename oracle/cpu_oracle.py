@@ -19,11 +19,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATHS = {
     ("flip", "ref"): os.path.join(_HERE, "_ref", "libref_flip.so"),
     ("euler", "ref"): os.path.join(_HERE, "_ref", "libref_euler.so"),
+    ("fluid3d", "ref"): os.path.join(_HERE, "_ref", "libref_fluid3d.so"),
+    ("fluid3d", "port"): os.path.join(_HERE, "_build", "liboracle.so"),
     ("flip", "port"): os.path.join(_HERE, "_build", "liboracle.so"),
     ("euler", "port"): os.path.join(_HERE, "_build", "liboracle.so"),
 }
 _PREFIX = {("flip", "ref"): "refflip_", ("flip", "port"): "orcflip_",
-           ("euler", "ref"): "refeuler_", ("euler", "port"): "orceuler_"}
+           ("euler", "ref"): "refeuler_", ("euler", "port"): "orceuler_",
+           ("fluid3d", "ref"): "reffluid3d_", ("fluid3d", "port"): "orcfluid3d_"}
 
 
 def build(quiet=True):
@@ -235,6 +238,87 @@ class EulerOracle:
         ph = (C.c_double * 2)()
         fn(self.h_, iters, dt, n_steps, ph)
         return list(ph) if timed else None
+
+
+class Fluid3DOracle:
+    """CPU 3D Eulerian smoke solver (eulerian_fluid/src/fluid3d.h:135-367); arrays are numpy views shaped (num_z, num_y, num_x)
+    -- x fastest like ix(i,j,k) = i + num_x*j + num_y*num_x*k (:131-133)."""
+
+    def __init__(self, x, y, z, density, h, kind=None):
+        kind = kind or best_kind("fluid3d")
+        self.kind = kind
+        self.lib = C.CDLL(_PATHS[("fluid3d", kind)])
+        self._p = _PREFIX[("fluid3d", kind)]
+        fn = self._fn("create"); fn.restype = C.c_void_p; fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+        self.h_ = C.c_void_p(fn(x, y, z, density, h))
+        ints = (C.c_int * 4)(); fl = (C.c_float * 2)()
+        d = self._fn("dims"); d.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        d(self.h_, ints, fl)
+        self.num_x, self.num_y, self.num_z, self.num_cells = list(ints)
+        self.density, self.h = [_f32(v) for v in fl]
+        ptr = self._fn("ptr"); ptr.restype = C.c_void_p; ptr.argtypes = [C.c_void_p, C.c_char_p]
+        shape = (self.num_z, self.num_y, self.num_x)
+        for name in ("u", "v", "w", "new_u", "new_v", "new_w", "pressure", "m", "new_m"):
+            a = np.ctypeslib.as_array(C.cast(ptr(self.h_, name.encode()), C.POINTER(C.c_float)), shape=(self.num_cells,))
+            setattr(self, name, a.reshape(shape))
+        a = np.ctypeslib.as_array(C.cast(ptr(self.h_, b"solid"), C.POINTER(C.c_ubyte)), shape=(self.num_cells,))
+        self.solid = a.reshape(shape)
+
+    def _fn(self, name):
+        return getattr(self.lib, self._p + name)
+
+    def close(self):
+        if self.h_:
+            fn = self._fn("destroy"); fn.argtypes = [C.c_void_p]; fn(self.h_); self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, iters, dt):
+        fn = self._fn("solve"); fn.argtypes = [C.c_void_p, C.c_int, C.c_float]; fn(self.h_, iters, dt)
+
+    def extrapolate(self):
+        fn = self._fn("extrapolate"); fn.argtypes = [C.c_void_p]; fn(self.h_)
+
+    def advect_vel(self, dt):
+        fn = self._fn("advect_vel"); fn.argtypes = [C.c_void_p, C.c_float]; fn(self.h_, dt)
+
+    def advect_smoke(self, dt):
+        fn = self._fn("advect_smoke"); fn.argtypes = [C.c_void_p, C.c_float]; fn(self.h_, dt)
+
+    def sample(self, x, y, z, field):
+        fn = self._fn("sample"); fn.restype = C.c_float; fn.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int]
+        return fn(self.h_, x, y, z, field)
+
+    def step(self, iters, dt, n_steps=1):
+        fn = self._fn("step"); fn.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]; fn(self.h_, iters, dt, n_steps)
+
+
+def make_fluid3d_scene(x=30, y=22, z=26, oracle_kind=None, seed=7):
+    """A wind-tunnel-like 3D scene in the spirit of fluid_ui.h:64-89: inflow u at i=1, solid walls on every face except the
+    outflow face, a solid ball, a smoke inlet patch, plus a seeded velocity perturbation so that every term of the advection is
+    exercised.  (fluid3d.h has no UI shell; num_z >= num_y keeps the reference's k < num_y loop bound in range, :311.)"""
+    o = Fluid3DOracle(x, y, z, 1000.0, 1 / 50.0, kind=oracle_kind)
+    nx, ny, nz = o.num_x, o.num_y, o.num_z
+    rng = np.random.default_rng(seed)
+    o.solid[:] = 0
+    o.solid[:, :, 0] = 1; o.solid[:, 0, :] = 1; o.solid[:, -1, :] = 1; o.solid[0, :, :] = 1; o.solid[-1, :, :] = 1
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ball = (i - nx // 3) ** 2 + (j - ny // 2) ** 2 + (k - nz // 2) ** 2 < (min(nx, ny, nz) // 5) ** 2
+    ball[:, :, 0] = ball[:, :, -1] = False
+    o.solid[ball] = 1
+    o.u[:] = (0.3 * rng.standard_normal(o.u.shape)).astype(np.float32)
+    o.v[:] = (0.3 * rng.standard_normal(o.u.shape)).astype(np.float32)
+    o.w[:] = (0.3 * rng.standard_normal(o.u.shape)).astype(np.float32)
+    o.u[:, :, 1] = 2.0
+    for a in (o.u, o.v, o.w):
+        a[o.solid != 0] = 0.0
+    o.m[:] = 1.0
+    o.m[nz // 2 - 2:nz // 2 + 3, ny // 2 - 2:ny // 2 + 3, 0:2] = 0.0
+    return o
 
 
 # --------------------------------------------------------------------------------------

@@ -6,9 +6,9 @@ bench.py; the C++ mirror is simsandgames_b200/host/flip_fluid_gpu.hpp.  There is
 importing works anywhere, creating a simulation without the built library or without a CUDA
 device raises.
 """
-from .binding import (FlipFluidGPU, FluidGPU, FlipGpuError, lib_path, load_library, build_library,
+from .binding import (FlipFluidGPU, FluidGPU, Fluid3DGPU, FlipGpuError, lib_path, load_library, build_library,
                       ShardedProjection, FlipFluidSharded, nccl_unique_id, slab_rows, FLIP_FIELDS, EULER_FIELDS, RED_BLACK, LEX_WAVEFRONT, LEX_DIAGONAL, LEX_SYSTOLIC)
 from . import scenes
 
-__all__ = ["FlipFluidGPU", "FluidGPU", "FlipGpuError", "lib_path", "load_library", "build_library", "ShardedProjection", "FlipFluidSharded", "nccl_unique_id", "slab_rows",
+__all__ = ["FlipFluidGPU", "FluidGPU", "Fluid3DGPU", "FlipGpuError", "lib_path", "load_library", "build_library", "ShardedProjection", "FlipFluidSharded", "nccl_unique_id", "slab_rows",
            "FLIP_FIELDS", "EULER_FIELDS", "RED_BLACK", "LEX_WAVEFRONT", "LEX_DIAGONAL", "LEX_SYSTOLIC", "scenes"]

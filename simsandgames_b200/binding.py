@@ -399,6 +399,86 @@ class FluidGPU:
             pass
 
 
+FLUID3D_FIELDS = {"u": (0, np.float32), "v": (1, np.float32), "w": (2, np.float32), "new_u": (3, np.float32), "new_v": (4, np.float32),
+                  "new_w": (5, np.float32), "pressure": (6, np.float32), "m": (7, np.float32), "new_m": (8, np.float32), "solid": (9, np.uint8)}
+
+
+class _Fluid3DDims(C.Structure):
+    _fields_ = [("num_x", C.c_int), ("num_y", C.c_int), ("num_z", C.c_int), ("num_cells", C.c_int), ("density", C.c_float), ("h", C.c_float)]
+
+
+class Fluid3DGPU:
+    """Fluid3D(x, y, z, d, h) -- eulerian_fluid/src/fluid3d.h:40 -- with its state in B200 HBM; arrays cross the boundary in the
+    reference layout ix(i,j,k) = i + num_x*j + num_y*num_x*k, i.e. numpy shape (num_z, num_y, num_x)."""
+    U_FIELD, V_FIELD, W_FIELD, S_FIELD = 0, 1, 2, 3  # fluid3d.h:31-36
+
+    def __init__(self, x, y, z, density, h, device=-1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check(self._lib.fluid3d_create(int(x), int(y), int(z), C.c_float(density), C.c_float(h), int(device), C.byref(self._h)), "fluid3d_create")
+        d = _Fluid3DDims()
+        _check(self._lib.fluid3d_get_dims(self._h, C.byref(d)), "fluid3d_get_dims")
+        self.num_x, self.num_y, self.num_z, self.num_cells = d.num_x, d.num_y, d.num_z, d.num_cells
+        self.density, self.h = np.float32(d.density), np.float32(d.h)
+
+    def ix(self, i, j, k):  # fluid3d.h:131-133
+        return i + self.num_x * j + self.num_y * self.num_x * k
+
+    def upload(self, name, array):
+        fid, dt = FLUID3D_FIELDS[name]
+        a, p = _as_c(np.asarray(array).reshape(-1), dt)
+        _check(self._lib.fluid3d_upload(self._h, fid, p, C.c_size_t(a.size)), f"fluid3d_upload({name})")
+
+    def readback(self, name):
+        fid, dt = FLUID3D_FIELDS[name]
+        out = np.empty(self.num_cells, dt)
+        _check(self._lib.fluid3d_readback(self._h, fid, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.size)), f"fluid3d_readback({name})")
+        return out.reshape(self.num_z, self.num_y, self.num_x)
+
+    def solveIncompressibility(self, num_iter, dt, solver_order=LEX_WAVEFRONT):
+        _check(self._lib.fluid3d_project(self._h, int(num_iter), C.c_float(dt), int(solver_order)), "fluid3d_project")
+
+    def extrapolate(self):
+        _check(self._lib.fluid3d_extrapolate(self._h), "fluid3d_extrapolate")
+
+    def advectVel(self, dt):
+        _check(self._lib.fluid3d_advect_vel(self._h, C.c_float(dt)), "fluid3d_advect_vel")
+
+    def advectSmoke(self, dt):
+        _check(self._lib.fluid3d_advect_smoke(self._h, C.c_float(dt)), "fluid3d_advect_smoke")
+
+    def step(self, num_iter, dt, n_steps=1, solver_order=LEX_WAVEFRONT):
+        _check(self._lib.fluid3d_step(self._h, int(num_iter), C.c_float(dt), int(solver_order), int(n_steps)), "fluid3d_step")
+
+    def sampleField(self, xs, ys, zs, field):
+        xs, ys, zs = (np.ascontiguousarray(a, np.float32).reshape(-1) for a in (xs, ys, zs))
+        out = np.empty_like(xs)
+        P = C.POINTER(C.c_float)
+        _check(self._lib.fluid3d_sample_field(self._h, int(field), xs.ctypes.data_as(P), ys.ctypes.data_as(P), zs.ctypes.data_as(P),
+                                              out.ctypes.data_as(P), C.c_size_t(xs.size)), "fluid3d_sample_field")
+        return out
+
+    def synchronize(self):
+        _check(self._lib.fluid3d_synchronize(self._h), "fluid3d_synchronize")
+
+    @property
+    def launch_count(self):
+        n = C.c_longlong()
+        _check(self._lib.fluid3d_get_launch_count(self._h, C.byref(n)), "fluid3d_get_launch_count")
+        return n.value
+
+    def close(self):
+        if self._h:
+            self._lib.fluid3d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 SHARD_FIELDS = {"vel_fast": (0, np.float32), "vel_slow": (1, np.float32), "p": (2, np.float32), "s": (3, np.float32),
                 "density": (4, np.float32), "cell_type": (5, np.int32)}
 

@@ -48,10 +48,23 @@ def euler_case(x, y, iters, checkpoints=(1, 10, 40)):
     return out
 
 
+def fluid3d_case(x, y, z, iters, checkpoints=(1, 4)):
+    o = co.make_fluid3d_scene(x, y, z, oracle_kind="ref")
+    out = {"dims": dict(num_x=o.num_x, num_y=o.num_y, num_z=o.num_z), "scene": {n: sha(getattr(o, n)) for n in ("u", "v", "w", "m", "solid")},
+           "iters": iters, "steps": {}}
+    done = 0
+    for c in checkpoints:
+        o.step(iters, 1 / 60.0, n_steps=c - done); done = c
+        out["steps"][str(c)] = {n: sha(getattr(o, n)) for n in ("u", "v", "w", "m", "pressure")}
+        out["steps"][str(c)]["m_mean"] = float(o.m.astype(np.float64).mean())
+    return out
+
+
 if __name__ == "__main__":
     assert co.available("flip", "ref"), "build oracle/_ref first (make -C oracle) -- needs /root/reference"
     gold = {"flip_default": flip_case("default"), "flip_synthetic_64": flip_case("synthetic", N=64, checkpoints=(1, 5, 12)),
-            "euler_96x72": euler_case(96, 72, 40), "euler_33x20": euler_case(33, 20, 7, checkpoints=(1, 5))}
+            "euler_96x72": euler_case(96, 72, 40), "euler_33x20": euler_case(33, 20, 7, checkpoints=(1, 5)),
+            "fluid3d_30x22x26": fluid3d_case(30, 22, 26, 20), "fluid3d_12x9x17": fluid3d_case(12, 9, 17, 5, checkpoints=(1, 3))}
     with open(os.path.join(HERE, "reference_golden.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "reference_golden.json"))

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "flipgpu.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:flip|euler|flipgpu)_[a-z_0-9]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b((?:flip|euler|flipgpu|fluid3d|sorshard)_[a-z_0-9]+)\s*\(", src)))
 
 
 def test_header_declares_the_expected_surface():

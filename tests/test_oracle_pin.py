@@ -105,3 +105,31 @@ def test_euler_set_obstacle_restatements_agree(kind, has_ref):
         co.euler_set_obstacle(b, x, y, r, np.float32(vx), np.float32(vy))
         for n in ("solid", "m", "u", "v"):
             assert np.array_equal(getattr(a, n), getattr(b, n)), (kind, n, x, y, r)
+
+
+def test_fluid3d_port_pinned_to_reference_and_goldens(has_ref):
+    """eulerian_fluid/src/fluid3d.h: the C port equals the reference header run here (when oracle/_ref is built) and the
+    committed hashes of the reference's own output -- project / extrapolate / advectVel (incl. its k < num_y bound) / advectSmoke."""
+    import hashlib, json, os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for key, (x, y, z) in (("fluid3d_30x22x26", (30, 22, 26)), ("fluid3d_12x9x17", (12, 9, 17))):
+        rec = gold[key]
+        o = co.make_fluid3d_scene(x, y, z, oracle_kind="port")
+        assert (o.num_x, o.num_y, o.num_z) == (rec["dims"]["num_x"], rec["dims"]["num_y"], rec["dims"]["num_z"])
+        for n, hsh in rec["scene"].items():
+            assert sha(getattr(o, n)) == hsh, (key, "scene", n)
+        done = 0
+        for c in sorted(rec["steps"], key=int):
+            o.step(rec["iters"], 1 / 60.0, n_steps=int(c) - done); done = int(c)
+            for n in ("u", "v", "w", "m", "pressure"):
+                assert sha(getattr(o, n)) == rec["steps"][c][n], (key, c, n)
+    if has_ref and co.available("fluid3d", "ref"):
+        a, b = co.make_fluid3d_scene(oracle_kind="ref"), co.make_fluid3d_scene(oracle_kind="port")
+        for fn, args in (("solve", (15, 1 / 60)), ("extrapolate", ()), ("advect_vel", (1 / 60,)), ("advect_smoke", (1 / 60,)), ("step", (9, 1 / 60, 4))):
+            getattr(a, fn)(*args); getattr(b, fn)(*args)
+            for n in ("u", "v", "w", "m", "pressure", "new_u", "new_m"):
+                assert np.array_equal(getattr(a, n).view(np.int32), getattr(b, n).view(np.int32)), (fn, n)
+        for q in [(0.21, 0.2, 0.33), (0.0, 5.0, 0.1), (0.55, 0.02, 0.61)]:
+            for fld in range(4):
+                assert a.sample(*q, fld) == b.sample(*q, fld)
