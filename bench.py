@@ -511,6 +511,31 @@ def s3_bench(args, rank, world, local_rank, N=16384):
     dist.destroy_process_group()
 
 
+def s0_default_tank(local_rank, steps=1000):
+    """BASELINE configs[0]: the reference's own default tank (134 x 101 cells, 19 092 particles), 1000 steps -- the launch-bound end of
+    the range: the whole step replayed as one CUDA graph vs queued launch by launch (the CPU reference takes 17.5 ms per step here)."""
+    import torch
+    import simsandgames_b200 as sg
+    out = {"workload": "flip_fluid default tank 134x101 cells, 19092 particles, simulate(1/60, 9.81, .9, 50, 2, 1.9, true, true, ...), 1000 steps (BASELINE configs[0])"}
+    for label, graphs in (("cuda_graph", True), ("launch_by_launch", False)):
+        sim, kw, geo = sg.scenes.make_flip_tank("default", device=local_rank)
+        sim.set_graph_mode(graphs)
+        stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+        sim.simulate(**kw, n_steps=20, update_colors=False)
+        sim.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        sim.simulate(**kw, n_steps=steps, update_colors=False)
+        e1.record(stream)
+        sim.synchronize(); torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 1e3 * wall) / steps
+        out[label] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "particle_steps_per_s": sim.num_particles * 1e3 / ms, "graph_replays": sim.graph_replays}
+        sim.close()
+    return out
+
+
 def s4_single_gpu(local_rank, steps=4, warmup=3, N=8192):
     """BASELINE configs[4] on ONE GPU: 8192^2 cells with the disc obstacle, 257 311 935 particles, 200 SOR iterations per step."""
     import torch
@@ -827,6 +852,10 @@ def product_arm(args, rank, world, local_rank):
     if world == 1:
         line["eulerian_s1"] = eulerian_bench(local_rank)
     if world == 1 and not args.no_extra_legs and N == BENCH_N:
+        try:
+            line["s0_default_tank"] = s0_default_tank(local_rank)
+        except Exception as exc:
+            line["s0_default_tank"] = {"error": str(exc)[:300]}
         try:
             line["s4_8192_obstacle"] = s4_single_gpu(local_rank)
         except Exception as exc:

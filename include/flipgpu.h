@@ -128,6 +128,11 @@ int flip_readback_wait(FlipSim* sim);
 int flip_set_obstacle(FlipSim* sim, float x, float y, float vx, float vy, float radius);
 /* n_steps x FlipFluid::simulate (flip_fluid.h:560-581); asynchronous on the handle's stream */
 int flip_step(FlipSim* sim, const FlipStepParams* sp, int n_steps);
+/* flip_step replays a captured whole-step CUDA graph once the simulation is in steady state (same parameters for two steps,
+ * rest density latched, reference solver order, no phase timers, nothing pending from the host); results are identical to the
+ * launch-by-launch path, the gain is launch overhead on small scenes.  on = 0 switches the replay off. */
+int flip_set_graph_mode(FlipSim* sim, int on);
+int flip_get_graph_replays(FlipSim* sim, long long* replays);
 /* single phases, for same-state replay tests (each cites its reference lines in flipgpu.cu) */
 int flip_phase_integrate(FlipSim* sim, float dt, float gravity);                    /* :156-162 */
 int flip_phase_bin(FlipSim* sim);                                                    /* :169-198 */

@@ -269,6 +269,15 @@ class FlipFluidGPU:
         _check(self._lib.flip_get_launch_count(self._h, C.byref(n)), "flip_get_launch_count")
         return n.value
 
+    def set_graph_mode(self, on=True):
+        _check(self._lib.flip_set_graph_mode(self._h, int(on)), "flip_set_graph_mode")
+
+    @property
+    def graph_replays(self):
+        n = C.c_longlong()
+        _check(self._lib.flip_get_graph_replays(self._h, C.byref(n)), "flip_get_graph_replays")
+        return n.value
+
     def solver_profile(self):
         """FLIPGPU_SOR_PROFILE=1: SM cycles the lexicographic solver spent per phase since the last call (8 counters)"""
         out = (C.c_ulonglong * 8)()

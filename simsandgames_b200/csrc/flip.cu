@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 #include "nccl_shim.cuh"
 
@@ -1061,6 +1062,20 @@ struct FlipSim {
 	bool ev_pending[kEvRing] = {false};
 	int ev_slot = 0;
 	LaunchCounter lc;
+	// Whole-step CUDA graph (single GPU, reference solver order, steady state): one captured simulate() per parity of the
+	// particle ping-pong buffers, replayed while nothing it depends on changes.  Small scenes are launch-bound (S0: ~25
+	// launches of a few microseconds each), which is what this removes; large scenes run the same graph without loss.
+	struct StepGraph {
+		cudaGraphExec_t exec = nullptr;
+		FlipStepParams sp{};
+		int np = -1;
+		bool s_binary = true;
+		long long launches = 0;
+	} graphs[2];
+	int eager_steps = 0;          // eager steps with unchanged parameters since the last change (allocations, plans, latches settle)
+	FlipStepParams last_sp{};
+	bool graphs_on = true;        // FLIPGPU_GRAPH=0 switches the replay off (A/B timing)
+	long long graph_replays = 0;
 };
 
 namespace {
@@ -1159,8 +1174,12 @@ int unsort(FlipSim* f) {
 	return FLIPGPU_OK;
 }
 
+// Phase boundary: CUDA event for the per-phase timers (flip_enable_timings) and an NVTX range for nsys / ncu timelines.
+const char* const kPhaseNames[FLIP_PH_COUNT + 1] = {"flip:integrate_bin", "flip:separate", "flip:collide_mark", "flip:p2g", "flip:solve", "flip:g2p", "flip:colors", nullptr};
 void phase_mark(FlipSim* f, int idx) {
 	if (f->timings_on) cudaEventRecord(f->ev[f->ev_slot][idx], f->st);
+	if (idx > 0) nvtxRangePop();
+	if (kPhaseNames[idx]) nvtxRangePushA(kPhaseNames[idx]);
 }
 void collect_slot(FlipSim* f, int slot) {
 	if (!f->ev_pending[slot]) return;
@@ -1797,6 +1816,7 @@ int flip_destroy(FlipSim* f) {
 	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->gcount, f->gfirst, f->count, f->u_alt, f->v_alt, f->p_alt,
 	                f->first, f->tile_sum, f->d_rest, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
+	for (auto& G : f->graphs) if (G.exec) cudaGraphExecDestroy(G.exec);
 	if (f->comm) g_nccl.CommDestroy(f->comm);
 	for (int k = 0; k < 2; k++) { cudaFree(f->send_pos[k]); cudaFree(f->send_vel[k]); cudaFree(f->send_id[k]); }
 	cudaFree(f->d_counters);
@@ -1969,6 +1989,59 @@ int flip_set_obstacle(FlipSim* f, float x, float y, float vx, float vy, float ra
 	return FLIPGPU_OK;
 }
 
+// one simulate(), flip_fluid.h:566-580 (Q11: one sub-step), queued on the handle's stream
+static int one_step(FlipSim* f, const FlipStepParams* sp, float cp, bool stage_frame) {
+	phase_mark(f, FLIP_PH_INTEGRATE_BIN);
+	FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));
+	phase_mark(f, FLIP_PH_SEPARATE);
+	// the last sweep runs the collision / marking pass itself (same device functions, identical results)
+	const bool fused = sp->separate_particles && sp->num_particle_iters >= 1 && !f->exact_order && f->d.num_particles > 0;
+	const FuseCollide fc{sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius};
+	if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0, fused ? &fc : nullptr));
+	phase_mark(f, FLIP_PH_COLLIDE_MARK);
+	FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius, fused));
+	phase_mark(f, FLIP_PH_P2G);
+	FG_TRY(p2g(f));
+	phase_mark(f, FLIP_PH_SOLVE);
+	FG_TRY(solve(f, sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0, sp->solver_order));
+	phase_mark(f, FLIP_PH_G2P);
+	FG_TRY(g2p(f, sp->flip_ratio, stage_frame));   // frame mode: + the caller-order copy of the positions
+	phase_mark(f, FLIP_PH_COLORS);
+	if (sp->update_colors) FG_TRY(colors(f));
+	phase_mark(f, FLIP_PH_COUNT);
+	return FLIPGPU_OK;
+}
+
+// Replay (or first capture) of the whole-step graph for the current ping-pong parity.  Capture runs one_step() with the
+// stream in capture mode: nothing executes, the host-side state advances exactly as in an eager step, and the graph is then
+// launched once.  A replay launches the stored graph and applies the same host-side state changes.
+static int graph_step(FlipSim* f, const FlipStepParams* sp, float cp) {
+	FlipSim::StepGraph& G = f->graphs[f->cur];
+	const bool fresh = !G.exec || memcmp(&G.sp, sp, sizeof(*sp)) != 0 || G.np != f->d.num_particles || G.s_binary != f->s_binary;
+	if (fresh) {
+		if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+		cudaGraph_t graph = nullptr;
+		const long long l0 = f->lc.n;
+		FG_CUDA(cudaStreamBeginCapture(f->st, cudaStreamCaptureModeThreadLocal));
+		const int rc = one_step(f, sp, cp, false);
+		const cudaError_t e = cudaStreamEndCapture(f->st, &graph);
+		if (rc != FLIPGPU_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+		FG_CUDA(e);
+		const cudaError_t ei = cudaGraphInstantiate(&G.exec, graph, 0);
+		cudaGraphDestroy(graph);
+		FG_CUDA(ei);
+		G.sp = *sp; G.np = f->d.num_particles; G.s_binary = f->s_binary; G.launches = f->lc.n - l0;
+		FG_CUDA(cudaGraphLaunch(G.exec, f->st));
+		return FLIPGPU_OK;
+	}
+	FG_CUDA(cudaGraphLaunch(G.exec, f->st));
+	f->cur = 1 - f->cur;            // what integrate_and_bin / positions_will_change do on the host
+	f->identity = false; f->bins_valid = true; f->staged_valid = false;
+	f->lc.n += G.launches;
+	f->graph_replays++;
+	return FLIPGPU_OK;
+}
+
 int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 	FG_CHECK(f && sp, FLIPGPU_EINVAL, "flip_step: null argument");
 	FG_CHECK(sp->num_pressure_iters >= 0 && sp->num_particle_iters >= 0 && sp->dt > 0, FLIPGPU_EINVAL, "flip_step: bad params");
@@ -1978,33 +2051,36 @@ int flip_step(FlipSim* f, const FlipStepParams* sp, int n_steps) {
 		for (int k = 0; k < n_steps; k++) FG_TRY(shard_step(f, sp));
 		return FLIPGPU_OK;
 	}
+	if (memcmp(&f->last_sp, sp, sizeof(*sp)) != 0) { f->last_sp = *sp; f->eager_steps = 0; }
 	for (int k = 0; k < n_steps; k++) {
 		if (f->timings_on) collect_slot(f, f->ev_slot);
 		if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
-		// simulate(), flip_fluid.h:566-580 (Q11: one sub-step)
-		phase_mark(f, FLIP_PH_INTEGRATE_BIN);
-		FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));
-		phase_mark(f, FLIP_PH_SEPARATE);
-		// the last sweep runs the collision / marking pass itself (same device functions, identical results)
-		const bool fused = sp->separate_particles && sp->num_particle_iters >= 1 && !f->exact_order && f->d.num_particles > 0;
-		const FuseCollide fc{sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius};
-		if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, sp->update_colors != 0, fused ? &fc : nullptr));
-		phase_mark(f, FLIP_PH_COLLIDE_MARK);
-		FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius, fused));
-		phase_mark(f, FLIP_PH_P2G);
-		FG_TRY(p2g(f));
-		phase_mark(f, FLIP_PH_SOLVE);
-		FG_TRY(solve(f, sp->num_pressure_iters, cp, sp->over_relaxation, sp->compensate_drift != 0, sp->solver_order));
-		phase_mark(f, FLIP_PH_G2P);
-		FG_TRY(g2p(f, sp->flip_ratio, f->frame_mode && k == n_steps - 1));   // frame mode: + the caller-order copy of the positions
-		phase_mark(f, FLIP_PH_COLORS);
-		if (sp->update_colors) FG_TRY(colors(f));
-		phase_mark(f, FLIP_PH_COUNT);
+		const bool stage_frame = f->frame_mode && k == n_steps - 1;
+		// steady state (allocations made, solver planned, rest density latched, nothing pending from the host): replay the graph
+		const bool steady = f->graphs_on && f->eager_steps >= 2 && f->rest_seen && !f->timings_on && !f->exact_order && !f->s_check_pending &&
+		                    !f->upload_pending && !stage_frame && sp->solver_order == FLIP_SOLVER_LEX_WAVEFRONT && f->s_binary && f->d.num_particles > 0;
+		if (steady) {
+			FG_TRY(graph_step(f, sp, cp));
+			continue;
+		}
+		FG_TRY(one_step(f, sp, cp, stage_frame));
+		f->eager_steps++;
 		if (f->timings_on) {
 			f->ev_pending[f->ev_slot] = true;
 			f->ev_slot = (f->ev_slot + 1) % FlipSim::kEvRing;
 		}
 	}
+	return FLIPGPU_OK;
+}
+
+int flip_set_graph_mode(FlipSim* f, int on) {
+	FG_CHECK(f, FLIPGPU_EINVAL, "null handle");
+	f->graphs_on = on != 0;
+	return FLIPGPU_OK;
+}
+int flip_get_graph_replays(FlipSim* f, long long* replays) {
+	FG_CHECK(f && replays, FLIPGPU_EINVAL, "null argument");
+	*replays = f->graph_replays;
 	return FLIPGPU_OK;
 }
 

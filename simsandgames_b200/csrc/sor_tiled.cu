@@ -386,7 +386,10 @@ int sor_solve_tiled(SorWorkspace** wsp, const SorGrid& g, int iters, float cp, f
 	FG_CUDA(cudaMemsetAsync(w->act, 0, (size_t)w->na * w->nb, st));
 	sor_prep_kernel<<<wave_grid((size_t)g.nf * g.ns, 256), 256, 0, st>>>(g, use_drift, w->code, use_drift ? w->drift : nullptr, w->act, w->na, 0, (size_t)g.nf * g.ns);
 	FG_CUDA(cudaMemsetAsync(w->counter, 0, 4, st));
-	w->epoch++;
+	// the completion flags are cleared per solve (a constant "done" value keeps the launch arguments identical from step to
+	// step, so a captured whole-step CUDA graph stays valid)
+	FG_CUDA(cudaMemsetAsync(w->flags, 0, (size_t)w->ni * w->nj * w->nq * 4, st));
+	w->epoch = 1;
 	TiledArgs A;
 	A.nf = g.nf; A.ns = g.ns; A.vel_f = g.vel_f; A.vel_s = g.vel_s; A.p = g.p; A.code = w->code;
 	A.drift = use_drift ? w->drift : nullptr; A.tiles = w->tiles; A.n_tiles = w->n_tiles; A.ni = w->ni; A.nj = w->nj;

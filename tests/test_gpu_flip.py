@@ -468,6 +468,24 @@ def test_large_scene_properties(N):
     assert 0 < np.abs(pos.reshape(-1) - pos0).max() < 8 * h
 
 
+def test_whole_step_graph_replay_is_identical_to_launch_by_launch():
+    """the steady-state step replayed as a CUDA graph == the same steps queued launch by launch, bit for bit,
+    incl. a parameter change (re-capture) and an upload in between."""
+    runs = []
+    for graphs in (True, False):
+        sim, kw, g = sg.scenes.make_flip_tank("default")
+        sim.set_graph_mode(graphs)
+        sim.simulate(**kw, n_steps=30, update_colors=False)
+        sim.set_obstacle(2.6, 1.4, 0.5, 0.0, 0.15)
+        kw2 = dict(kw, obstacle_x=2.6, obstacle_y=1.4, obstacle_vel_x=0.5)
+        sim.simulate(**kw2, n_steps=15, update_colors=True)
+        sim.simulate(**kw2, n_steps=1, update_colors=True)
+        assert (sim.graph_replays > 30) == graphs, sim.graph_replays
+        runs.append({n: sim.readback(n).copy() for n in ("particle_pos", "particle_vel", "u", "v", "p", "cell_type", "particle_color", "cell_particle_ids")})
+    for n in runs[0]:
+        assert_bit_equal(runs[0][n], runs[1][n], f"graph replay vs launches: {n}")
+
+
 def test_async_readback_matches_blocking_readback():
     import torch
     sim, kw, g = sg.scenes.make_flip_tank("default")
