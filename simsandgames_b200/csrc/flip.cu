@@ -1641,9 +1641,12 @@ int shard_step(FlipSim* f, const FlipStepParams* sp) {
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
 	FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));         // owned + ghosts
 	phase_mark(f, FLIP_PH_SEPARATE);
-	if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, false));
+	// as in the one-GPU step, the last sweep runs the collision / marking pass itself (identical results)
+	const bool fused = sp->separate_particles && sp->num_particle_iters >= 1 && f->d.num_particles > 0;
+	const FuseCollide fc{sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius};
+	if (sp->separate_particles) FG_TRY(separate(f, sp->num_particle_iters, false, fused ? &fc : nullptr));
 	phase_mark(f, FLIP_PH_COLLIDE_MARK);
-	FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius));
+	FG_TRY(collide_mark(f, true, true, sp->obstacle_x, sp->obstacle_y, sp->obstacle_vel_x, sp->obstacle_vel_y, sp->obstacle_radius, fused));
 	phase_mark(f, FLIP_PH_P2G);
 	FG_TRY(p2g(f));                                                        // own node rows
 	{	// the rows next to the slab come from their owners: post-P2G fields, cell types, densities, s
