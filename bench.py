@@ -400,7 +400,7 @@ def shard_selfcheck(rank, world, local_rank, steps=6):
     return box[0]
 
 
-def synthetic_rank_lattice(N, j0, j1, build=True):
+def synthetic_rank_lattice(N, j0, j1, build=True, row_histogram=False):
     """The particles of the synthetic dam-break (SURVEY 8d rule; lattice of flip_fluid/src/main.cpp:47-66) whose cell row lies
     in grid rows [j0, j1), with their global caller indices p = i*num_y + j -- without materialising the other ranks' particles.
     Same fp32 expressions as flip_scene_tank and the device ownership test."""
@@ -420,6 +420,8 @@ def synthetic_rank_lattice(N, j0, j1, build=True):
     row = np.clip(((f32(1) / h_grid) * y).astype(np.int32), 0, N - 1)
     mine = jj[(row >= j0) & (row < j1)]
     out = dict(sp=sp, W=W, r=r, dt=dt, num_x=num_x, num_y=num_y, P_global=num_x * num_y, n_own=int(mine.size) * num_x, h_grid=h_grid)
+    if row_histogram:
+        out["row_particles"] = np.bincount(row, minlength=N).astype(np.float64) * num_x
     if build:
         ii = np.arange(num_x, dtype=np.float32)[:, None]
         pos = np.empty((num_x, mine.size, 2), np.float32)
@@ -442,11 +444,17 @@ def single_tank_sharded(args, rank, world, local_rank, N, with_obstacle=False, s
     steps = steps or args.steps
     iters = 200 if with_obstacle else 50
     uid = parallel.broadcast_unique_id()
-    j0, j1 = parallel.slab_partition(N, world)[rank]
+    # slabs balanced by estimated work per grid row: particles x (cost per particle) + cells x (cost per cell and sweep), both
+    # taken from the one-GPU phase timings at S2 (8.4 ms per 64.3 M particles, 4.4 ms per 16.8 M cells x 50 sweeps)
+    rows_p = synthetic_rank_lattice(N, 0, N, build=False, row_histogram=True)["row_particles"]
+    weights = rows_p * 1.31e-7 + N * (iters * 5.2e-9 + 2.0e-8)
+    row_starts = parallel.weighted_partition(weights, world, min_rows=16)
+    j0, j1 = row_starts[rank], row_starts[rank + 1]
     geo = synthetic_rank_lattice(N, j0, j1, build=False)
     sp, W, r, dt, num_x, num_y, P_global, n_own, h_grid = (geo[k] for k in ("sp", "W", "r", "dt", "num_x", "num_y", "P_global", "n_own", "h_grid"))
     cap = int(max(n_own * 1.25, 4.0e6)) + 2 * num_x * 64
-    sim = sg.FlipFluidSharded(1000.0, float(W), float(W), float(sp), float(r), cap, P_global, rank, world, unique_id=uid, device=local_rank)
+    sim = sg.FlipFluidSharded(1000.0, float(W), float(W), float(sp), float(r), cap, P_global, rank, world, unique_id=uid, device=local_rank,
+                              row_starts=row_starts)
     assert (sim.f_num_x, sim.f_num_y) == (N, N) and (sim.j0, sim.j1) == (j0, j1) and np.float32(sim.h) == h_grid, (sim.f_num_x, sim.j0, sim.h, h_grid)
     built = synthetic_rank_lattice(N, j0, j1, build=True)
     pos, ids = built["pos"], built["ids"]
@@ -497,7 +505,8 @@ def single_tank_sharded(args, rank, world, local_rank, N, with_obstacle=False, s
             "cell_updates_per_s_whole_step": float(N - 2) * (N - 2) * iters / s_per_step,
             "config": {"workload": f"flip_fluid synthetic dam-break {N}^2 grid, {P_global} particles, {iters} SOR iters" +
                                    (", static disc obstacle" if with_obstacle else "") + f", slab-sharded (BASELINE {name})",
-                       "grid": [N, N], "particles_per_gpu": owned, "solver_order": "red_black", "parallelism": f"y-slabs over {world} GPUs, NCCL halo/ghost exchange",
+                       "grid": [N, N], "particles_per_gpu": owned, "slab_row_starts": [int(x) for x in row_starts], "solver_order": "red_black",
+                       "parallelism": f"y-slabs over {world} GPUs (balanced by estimated work per row), NCCL halo/ghost exchange",
                        "gpu_mem_used_GB_rank0": round((mem[1] - mem[0]) / 1e9, 1)},
             "roofline": {"bound": "hbm", "kernel": "whole sharded step (all GPUs)", "achieved": step_bytes / s_per_step / 1e9 / world, "peak": peak,
                          "unit": "GB/s per GPU", "frac": step_bytes / s_per_step / 1e9 / world / peak, "traffic": None, "peak_source": peak_src}}

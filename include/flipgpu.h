@@ -240,6 +240,11 @@ int fluid3d_get_launch_count(Fluid3DSim* sim, long long* launches);
  * bit-identical to the one-GPU FLIP_SOLVER_RED_BLACK run (tests/test_gpu_multi.py).  params->max_particles is the
  * per-rank capacity (owned + ghosts).  Only FLIP_SOLVER_RED_BLACK, update_colors = 0. */
 int flip_create_sharded(const FlipParams* params, int global_particles, int rank, int nranks, const void* unique_id128, FlipSim** out);
+/* same with caller-chosen slabs: row_starts[0..nranks] ascending from 0 to f_num_y, rank r owns rows [row_starts[r], row_starts[r+1])
+ * (every slab at least halo_rows+1 rows); NULL = equal slabs.  Lets the caller balance a scene whose liquid does not fill the
+ * partition axis evenly (BASELINE configs[3]). */
+int flip_create_sharded_rows(const FlipParams* params, int global_particles, int rank, int nranks, const int* row_starts, const void* unique_id128,
+                             FlipSim** out);
 int flip_get_shard_info(FlipSim* sim, int* j0, int* j1, int* halo_rows, int* ghost_band_rows, long long* exchanges);
 int flip_upload_particles(FlipSim* sim, const float* pos, const float* vel /* may be NULL = 0 */, const int* global_ids, int n);
 int flip_readback_particles(FlipSim* sim, float* pos, float* vel, int* global_ids, int capacity, int* n_out);

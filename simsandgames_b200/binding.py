@@ -573,12 +573,17 @@ class FlipFluidSharded(FlipFluidGPU):
     window rows are current); particles are exchanged as (pos, vel, global id) triples."""
 
     def __init__(self, density, width, height, spacing, particle_radius, max_local_particles, global_particles, rank, nranks,
-                 unique_id=None, device=-1):
+                 unique_id=None, device=-1, row_starts=None):
         self._lib = load_library()
         self._h = C.c_void_p()
         pr = _FlipParams(density, width, height, spacing, particle_radius, max_local_particles, device)
         idbuf = (C.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
-        _check(self._lib.flip_create_sharded(C.byref(pr), int(global_particles), int(rank), int(nranks), idbuf, C.byref(self._h)), "flip_create_sharded")
+        rows = None
+        if row_starts is not None:   # caller-chosen slabs (load balance), else equal slabs
+            assert len(row_starts) == nranks + 1
+            rows = (C.c_int * (nranks + 1))(*[int(r) for r in row_starts])
+        _check(self._lib.flip_create_sharded_rows(C.byref(pr), int(global_particles), int(rank), int(nranks), rows, idbuf, C.byref(self._h)),
+               "flip_create_sharded_rows")
         self._refresh()
         self.rank, self.nranks = rank, nranks
         self.j0, self.j1, self.halo, self.band, _ = self.shard_info()

@@ -2090,6 +2090,12 @@ int flip_get_graph_replays(FlipSim* f, long long* replays) {
 
 // ------------------------------------------------------------------ slab-sharded FLIP
 int flip_create_sharded(const FlipParams* pr, int global_particles, int rank, int nranks, const void* unique_id128, FlipSim** out) {
+	return flip_create_sharded_rows(pr, global_particles, rank, nranks, nullptr, unique_id128, out);
+}
+// row_starts: nranks+1 ascending row numbers (0 ... f_num_y), rank r owns rows [row_starts[r], row_starts[r+1]); NULL = equal slabs.
+// Unequal slabs balance a scene whose liquid does not fill the partition axis evenly (BASELINE configs[3]: the top slabs are air).
+int flip_create_sharded_rows(const FlipParams* pr, int global_particles, int rank, int nranks, const int* row_starts, const void* unique_id128,
+                             FlipSim** out) {
 	FG_CHECK(pr && out && nranks >= 1 && rank >= 0 && rank < nranks && global_particles >= 0, FLIPGPU_EINVAL, "flip_create_sharded: bad argument");
 	FG_CHECK(nranks == 1 || unique_id128, FLIPGPU_EINVAL, "flip_create_sharded: a NCCL unique id is required for %d ranks", nranks);
 	FlipSim* f = nullptr;
@@ -2097,12 +2103,24 @@ int flip_create_sharded(const FlipParams* pr, int global_particles, int rank, in
 	DeviceGuard guard(f->device);
 	const int ny = f->d.f_num_y;
 	f->sharded = true; f->rank = rank; f->nranks = nranks;
-	f->j0 = (int)((long long)ny * rank / nranks);
-	f->j1 = (int)((long long)ny * (rank + 1) / nranks);
-	f->min_slab_rows = ny / nranks;
-	if (nranks > 1 && f->j1 - f->j0 < f->halo + 1) {
+	if (row_starts) {
+		bool ok = row_starts[0] == 0 && row_starts[nranks] == ny;
+		int min_rows = ny;
+		for (int r = 0; r < nranks && ok; r++) { ok = row_starts[r + 1] > row_starts[r]; min_rows = std::min(min_rows, row_starts[r + 1] - row_starts[r]); }
+		if (!ok) {
+			flip_destroy(f);
+			fg::set_error("flip_create_sharded_rows: row_starts must ascend from 0 to f_num_y = %d", ny);
+			return FLIPGPU_EINVAL;
+		}
+		f->j0 = row_starts[rank]; f->j1 = row_starts[rank + 1]; f->min_slab_rows = min_rows;
+	} else {
+		f->j0 = (int)((long long)ny * rank / nranks);
+		f->j1 = (int)((long long)ny * (rank + 1) / nranks);
+		f->min_slab_rows = ny / nranks;
+	}
+	if (nranks > 1 && f->min_slab_rows < f->halo + 1) {
 		flip_destroy(f);
-		fg::set_error("flip_create_sharded: %d rows over %d ranks leaves slabs thinner than the %d-row halo", ny, nranks, f->halo);
+		fg::set_error("flip_create_sharded: a slab of %d rows is thinner than the %d-row halo (%d rows over %d ranks)", f->min_slab_rows, f->halo, ny, nranks);
 		return FLIPGPU_EINVAL;
 	}
 	f->gy0 = std::max(f->j0 - f->halo, 0); f->gy1 = std::min(f->j1 + f->halo, ny);

@@ -29,3 +29,20 @@ def slab_partition(ns, nranks):
 def stitch_rows(parts):
     """Concatenate per-rank own-row blocks (in rank order) back into the global (ns, nf) array."""
     return np.concatenate(parts, axis=0)
+
+
+def weighted_partition(row_weights, nranks, min_rows=10):
+    """Row boundaries [r_0=0, ..., r_nranks=ns] that give every rank about the same total weight (a rank's work = its rows'
+    weights: particles x cost per particle + cells x cost per cell), with at least min_rows rows per slab (halo + 1)."""
+    w = np.asarray(row_weights, np.float64)
+    ns = w.size
+    assert ns >= nranks * min_rows
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    starts = [0]
+    for r in range(1, nranks):
+        j = int(np.searchsorted(c, c[-1] * r / nranks))
+        j = max(j, starts[-1] + min_rows)
+        j = min(j, ns - (nranks - r) * min_rows)
+        starts.append(j)
+    starts.append(ns)
+    return starts

@@ -16,8 +16,9 @@ def run_flip(d, out_prefix, rank, world, local, uid, sg):
     """this rank's slab of a sharded FLIP run: global scene in, owned particles + own grid rows out"""
     g = {k: float(d[k]) for k in ("density", "width", "height", "spacing", "radius")}
     pos, vel = d["pos"].reshape(-1, 2), d["vel"].reshape(-1, 2)
+    rows = [int(x) for x in d["row_starts"]] if "row_starts" in d.files else None     # caller-chosen (unequal) slabs
     sim = sg.FlipFluidSharded(g["density"], g["width"], g["height"], g["spacing"], g["radius"], int(d["capacity"]), pos.shape[0], rank, world,
-                              unique_id=uid, device=local)
+                              unique_id=uid, device=local, row_starts=rows)
     for name in ("s", "u", "v"):
         sim.upload(name, d[name])                      # grid arrays keep the global shape on every rank
     if float(d["rest"]) != 0.0:

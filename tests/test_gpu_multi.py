@@ -97,12 +97,13 @@ def _launch(tmp_path, world, inp):
     return [np.load(str(tmp_path / f"out_rank{k}.npz")) for k in range(world)]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world,rows", [(2, None), (4, None), (2, [0, 33, 101])])
 @pytest.mark.parametrize("start,steps,latch", [(0, 12, True), (40, 10, False)])
-def test_sharded_flip_step_matches_one_gpu(tmp_path, world, start, steps, latch):
+def test_sharded_flip_step_matches_one_gpu(tmp_path, world, rows, start, steps, latch):
     """The whole FLIP step, slab-sharded over `world` GPUs, against the one-GPU red-black run from the same state.
     With the rest density given (latch=False) every particle and every grid row is bit-identical; when the latch
-    runs inside the sharded step the cross-rank sum may round differently, so that case is compared to 1e-5."""
+    runs inside the sharded step the cross-rank sum may round differently, so that case is compared to 1e-5.
+    rows: caller-chosen unequal slabs (flip_create_sharded_rows, the load-balancing entry point)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     o, p, g = co.make_flip_scene("default", oracle_kind="port")
@@ -116,7 +117,8 @@ def test_sharded_flip_step_matches_one_gpu(tmp_path, world, start, steps, latch)
     one.simulate(**product_args(p), n_steps=steps, solver_order=sg.RED_BLACK, update_colors=False)
     inp = str(tmp_path / "in.npz")
     np.savez(inp, flip_steps=steps, pos=o.particle_pos[:2 * P], vel=o.particle_vel[:2 * P], s=o.s, u=o.u, v=o.v, rest=rest,
-             capacity=2 * P, dt=p["dt"], iters=50, ox=p["ox"], oy=p["oy"], orad=p["orad"], **{k: g[k] for k in ("density", "width", "height", "spacing", "radius")})
+             capacity=2 * P, dt=p["dt"], iters=50, ox=p["ox"], oy=p["oy"], orad=p["orad"], **({"row_starts": np.array(rows)} if rows else {}),
+             **{k: g[k] for k in ("density", "width", "height", "spacing", "radius")})
     parts = _launch(tmp_path, world, inp)
     ids = np.concatenate([pt["ids"] for pt in parts])
     assert np.array_equal(np.sort(ids), np.arange(P)), "every particle is owned by exactly one rank"
