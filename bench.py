@@ -26,9 +26,21 @@ sys.path.insert(0, ROOT)
 METRIC = "flip_particle_steps_per_s"
 UNIT = "particle-steps/s"
 BENCH_N = 4096
-TRAFFIC_NCU = 197.5e6  # bytes per launch: dram__bytes_read.sum (144.9 MB) + dram__bytes_write.sum (52.6 MB) of sor_gs_tiled_kernel<1,1,16>,
-                       # ncu --set full, profiles/r1_final_ncu_flip_4096.md (temporal blocking: ~150x below the algorithmic 30.2 GB)
+NCU_KERNELS_CSV = os.path.join("profiles", "r2_ncu_kernels.csv")   # per-kernel ncu --set full numbers of THIS workload (scripts/ncu_summary.py)
 WORKLOAD = "flip_fluid synthetic dam-break 4096^2 grid, 64264080 particles, 50 SOR iters, 2 separation sweeps (BASELINE configs[2])"
+
+
+def traffic_from_profile(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed ncu table (None if absent)."""
+    import csv
+    try:
+        with open(os.path.join(ROOT, NCU_KERNELS_CSV)) as f:
+            for row in csv.DictReader(f):
+                if row["kernel"].replace("fg::", "").startswith(kernel_prefix):
+                    return float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])
+    except Exception:
+        pass
+    return None
 
 
 def peaks():
@@ -485,6 +497,15 @@ def single_tank_sharded(args, rank, world, local_rank, N, with_obstacle=False, s
     sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    phases = None
+    if os.environ.get("FLIPGPU_BENCH_PHASES") == "1":   # extra untimed pass: every rank's CUDA-event phases (exchanges booked on the phase they feed)
+        sim.enable_timings(True); sim.reset_timings()
+        sim.simulate(**kw, n_steps=2)
+        sim.synchronize(); torch.cuda.synchronize(); dist.barrier()
+        mine = {k: round(v / 2, 3) for k, v in sim.timings().items()}
+        sim.enable_timings(False)
+        phases = [None] * world
+        dist.all_gather_object(phases, mine)
     h_out = torch.empty(2 * cap, dtype=torch.float32).pin_memory()
     n_now = sim.readback_owned_pos_into(h_out.data_ptr(), cap)
     cnt = torch.tensor([n_now, n_own], dtype=torch.int64, device="cuda"); dist.all_reduce(cnt)
@@ -502,6 +523,7 @@ def single_tank_sharded(args, rank, world, local_rank, N, with_obstacle=False, s
     name = "configs[4]" if with_obstacle else "configs[3]"
     return {"metric": METRIC, "value": P_global / s_per_step, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "phase_ms_per_step_by_rank": phases,
             "cell_updates_per_s_whole_step": float(N - 2) * (N - 2) * iters / s_per_step,
             "config": {"workload": f"flip_fluid synthetic dam-break {N}^2 grid, {P_global} particles, {iters} SOR iters" +
                                    (", static disc obstacle" if with_obstacle else "") + f", slab-sharded (BASELINE {name})",
@@ -849,9 +871,10 @@ def product_arm(args, rank, world, local_rank):
                 "what": "per frame: flip_upload_async(s) H2D (own stream, joined at the collision pass) + flip_step (its G2P kernel also writes the positions in caller order into a staging buffer) + flip_readback_pos_async(particle_pos) D2H into double-buffered pinned frames; the PCIe copy of frame k overlaps step k+1, every frame is waited for, the last frame's copy is not hidden"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "sor_gs_tiled_kernel (+ sor_prep_kernel; whole 50-iteration solve in one launch)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": TRAFFIC_NCU if (args.grid == BENCH_N and world == 1) else None,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload "
-                                       "(profiles/r1_final_ncu_flip_4096.md); temporal blocking keeps it ~150x below the algorithmic bytes",
+                     "frac": achieved / peak, "traffic": traffic_from_profile("sor_gs_tiled_kernel<(bool)1, (bool)1") if (args.grid == BENCH_N and world == 1) else None,
+                     "traffic_source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, read from {NCU_KERNELS_CSV} "
+                                       "(written by scripts/ncu_summary.py from the committed capture, profiles/r2_ncu_flip_4096.md); temporal blocking keeps it ~150x below the "
+                                       "algorithmic bytes, so frac > 1 is possible: step_roofline is the honest whole-step figure",
                      "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches},
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / s_per_step / 1e9, "unit": "GB/s",
                           "frac_of_measured": step_bytes / s_per_step / 1e9 / peak, "frac_of_8TBs": step_bytes / s_per_step / 8e12,

@@ -1,7 +1,10 @@
 """Turn the ncu exports of a gpurun call into the markdown committed under profiles/.
-usage: python scripts/ncu_summary.py <launches.csv> <raw.csv (ncu -i X.ncu-rep --page raw --csv)> <out.md> <title>"""
+usage: python scripts/ncu_summary.py <launches.csv> <raw.csv (ncu -i X.ncu-rep --page raw --csv)> <out.md> <title> [kernels.csv]
+kernels.csv (optional): one row per kernel -- time, DRAM bytes read / written per launch -- the table bench.py reads
+`roofline.traffic` from."""
 import csv, collections, sys
 launches, raw, out, title = sys.argv[1:5]
+kernels_csv = sys.argv[5] if len(sys.argv) > 5 else None
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
 hdr = rows[0]; ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 agg = collections.OrderedDict()
@@ -26,6 +29,7 @@ kn = h.index("Kernel Name")
 L += ["## `ncu --set full --clock-control none` (one launch of each kernel of a timed step)", "",
       "| kernel | " + " | ".join(f"{lab} [{units[i]}]" if units[i] else lab for i, lab in idx) + " |", "|---|" + "---:|" * len(idx)]
 seen = set()
+rr = rr[:2] + rr[:1:-1]          # newest launch of every kernel first: the steady-state one
 for r in rr[2:]:
     n = r[kn].split('(')[0].replace("void ", "")
     if n in seen: continue
@@ -36,3 +40,20 @@ for r in rr[2:]:
     L.append(f"| `{n}` | " + " | ".join(fmt(r[i]) for i, _ in idx) + " |")
 open(out, "w").write("\n".join(L) + "\n")
 print(out, "written")
+if kernels_csv:
+    def to_bytes(v, unit):
+        v = float(str(v).replace(',', ''))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+    def to_ms(v, unit):
+        v = float(str(v).replace(',', ''))
+        return v * {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(unit, 1)
+    it, ir, iw = h.index("gpu__time_duration.sum"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    seen = set()
+    with open(kernels_csv, "w") as f:
+        f.write("kernel,time_ms,dram_read_bytes,dram_write_bytes\n")
+        for r in rr[2:]:
+            n = r[kn].split('(')[0].replace("void ", "")
+            if n in seen: continue
+            seen.add(n)
+            f.write(f'"{n}",{to_ms(r[it], units[it]):.6f},{to_bytes(r[ir], units[ir]):.0f},{to_bytes(r[iw], units[iw]):.0f}\n')
+    print(kernels_csv, "written")
