@@ -18,42 +18,42 @@ L = [f"# {title}", "", "## Launch list (`ncu --metrics gpu__time_duration.sum --
 for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     L.append(f"| `{n}` | {c} | {t:.1f} | {t / c:.1f} | {t / tot:.3f} |")
 L += ["", f"{len(rows) - 1} launches, {tot / 1e3:.1f} ms of kernel time.", ""]
-rr = list(csv.reader(open(raw))); h, units = rr[0], rr[1]
-want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "DRAM rd"), ("dram__bytes_write.sum", "DRAM wr"),
+# one or more raw exports (comma separated); every file has its own unit row, so everything is normalised here
+TIME = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3, "nsecond": 1e-6}
+BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+want = [("gpu__time_duration.sum", "time [ms]"), ("dram__bytes_read.sum", "DRAM rd [GB]"), ("dram__bytes_write.sum", "DRAM wr [GB]"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps act %"), ("launch__registers_per_thread", "regs"),
         ("smsp__inst_executed.sum", "warp inst"), ("smsp__thread_inst_executed_per_inst_executed.ratio", "lanes/inst"),
         ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %")]
-idx = [(h.index(w), lab) for w, lab in want if w in h]
-kn = h.index("Kernel Name")
-L += ["## `ncu --set full --clock-control none` (one launch of each kernel of a timed step)", "",
-      "| kernel | " + " | ".join(f"{lab} [{units[i]}]" if units[i] else lab for i, lab in idx) + " |", "|---|" + "---:|" * len(idx)]
-seen = set()
-rr = rr[:2] + rr[:1:-1]          # newest launch of every kernel first: the steady-state one
-for r in rr[2:]:
-    n = r[kn].split('(')[0].replace("void ", "")
-    if n in seen: continue
-    seen.add(n)
-    def fmt(x):
-        try: return f"{float(x):.4g}"
-        except ValueError: return x
-    L.append(f"| `{n}` | " + " | ".join(fmt(r[i]) for i, _ in idx) + " |")
+def num(x):
+    return float(str(x).replace(',', ''))
+records = collections.OrderedDict()   # kernel -> {label: value}; later files / later launches overwrite (steady state)
+for path in raw.split(","):
+    rr = list(csv.reader(open(path))); h, units = rr[0], rr[1]
+    kn = h.index("Kernel Name")
+    for r in rr[2:]:
+        n = r[kn].split('(')[0].replace("void ", "").replace("fg::", "")
+        rec = {}
+        for w, lab in want:
+            if w not in h: continue
+            i = h.index(w)
+            try: v = num(r[i])
+            except ValueError: continue
+            if lab.startswith("time"): v *= TIME.get(units[i], 1.0)
+            elif "[GB]" in lab: v *= BYTES.get(units[i], 1.0) / 1e9
+            rec[lab] = v
+        records[n] = rec
+labs = [lab for _, lab in want]
+L += ["## `ncu --set full --clock-control none` (the launch of each kernel in a steady-state step; scripts/ncu_target.py)", "",
+      "| kernel | " + " | ".join(labs) + " |", "|---|" + "---:|" * len(labs)]
+for n, rec in records.items():
+    L.append(f"| `{n}` | " + " | ".join(f"{rec[l]:.4g}" if l in rec else "" for l in labs) + " |")
 open(out, "w").write("\n".join(L) + "\n")
 print(out, "written")
 if kernels_csv:
-    def to_bytes(v, unit):
-        v = float(str(v).replace(',', ''))
-        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
-    def to_ms(v, unit):
-        v = float(str(v).replace(',', ''))
-        return v * {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}.get(unit, 1)
-    it, ir, iw = h.index("gpu__time_duration.sum"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
-    seen = set()
     with open(kernels_csv, "w") as f:
         f.write("kernel,time_ms,dram_read_bytes,dram_write_bytes\n")
-        for r in rr[2:]:
-            n = r[kn].split('(')[0].replace("void ", "")
-            if n in seen: continue
-            seen.add(n)
-            f.write(f'"{n}",{to_ms(r[it], units[it]):.6f},{to_bytes(r[ir], units[ir]):.0f},{to_bytes(r[iw], units[iw]):.0f}\n')
+        for n, rec in records.items():
+            f.write(f'"{n}",{rec.get("time [ms]", 0):.6f},{rec.get("DRAM rd [GB]", 0) * 1e9:.0f},{rec.get("DRAM wr [GB]", 0) * 1e9:.0f}\n')
     print(kernels_csv, "written")
