@@ -567,6 +567,36 @@ def s0_default_tank(local_rank, steps=1000):
     return out
 
 
+def developed_flow(local_rank, N=BENCH_N, steps=6):
+    """The same S2 scene in a DEVELOPED state: seeded velocity noise (sigma 0.6, ~1.7 radii of random motion per step) on top of the
+    lattice, three steps to let it splash -- crowded hash cells (up to ~10 particles), multi-cell moves, no lattice regularity -- then
+    `steps` timed steps.  The headline times steps 4-15 of the dam-break, a near-lattice state; this leg says what disorder costs."""
+    import numpy as np
+    import torch
+    import simsandgames_b200 as sg
+    sim, kw, geo = sg.scenes.make_flip_tank("synthetic", N=N, device=local_rank)
+    P = sim.num_particles
+    rng = np.random.default_rng(20261020)
+    sim.upload("particle_vel", rng.normal(0.0, 0.6, 2 * P).astype(np.float32))
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
+    sim.simulate(**kw, n_steps=3, update_colors=False)
+    sim.synchronize()
+    sim.enable_timings(True); sim.reset_timings()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sim.simulate(**kw, n_steps=steps, update_colors=False)
+    e1.record(stream)
+    sim.synchronize(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ph = {k: v / steps for k, v in sim.timings().items()}
+    sim.enable_timings(False)
+    cnt = sim.readback("num_cell_particles")
+    out = {"workload": f"S2 scene with seeded velocity noise (sigma 0.6), steps 4-{3 + steps}", "ms_per_step": ms, "value": P / (ms * 1e-3), "unit": UNIT,
+           "phase_ms_per_step": ph, "max_particles_per_hash_cell": int(cnt.max()), "hash_cells_with_3_or_more": int((cnt >= 3).sum())}
+    sim.close()
+    return out
+
+
 def s4_single_gpu(local_rank, steps=4, warmup=3, N=8192):
     """BASELINE configs[4] on ONE GPU: 8192^2 cells with the disc obstacle, 257 311 935 particles, 200 SOR iterations per step."""
     import torch
@@ -860,7 +890,7 @@ def product_arm(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD if N == BENCH_N else f"flip_fluid synthetic dam-break {N}^2 (non-default --grid)",
                    "grid": [nx, ny], "particles_per_gpu": P, "pressure_iters": iters, "separation_sweeps": 2,
                    "solver_order": "lexicographic (blocked wavefront, bit-identical to the reference order)", "colours": "off (render state, SURVEY 8d)",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent tanks, one per GPU (particle sharding is not built yet; the slab-sharded solver with NCCL halo exchange is reported under sharded_solver)",
+                   "parallelism": "1 GPU",
                    "reseed": f"state re-seeded (untimed, +{args.warmup} warm-up steps) every {SEG} timed steps: the dam-break rule diverges in the reference itself after ~15 steps (profiles/r1_stability.md)",
                    "l2": "working set ~4.7 GB per step >> 126 MB L2 (no flush needed)",
                    "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
@@ -875,7 +905,10 @@ def product_arm(args, rank, world, local_rank):
                      "traffic_source": f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload, read from {NCU_KERNELS_CSV} "
                                        "(written by scripts/ncu_summary.py from the committed capture, profiles/r2_ncu_flip_4096.md); temporal blocking keeps it ~150x below the "
                                        "algorithmic bytes, so frac > 1 is possible: step_roofline is the honest whole-step figure",
-                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches},
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes_per_launch, "launch_us": launch_s * 1e6, "launches_per_step": n_solver_launches,
+                     "note": "achieved = the reference loop's cell visits x 36 B (SURVEY 8d) over the launch time: reference-equivalent work, not DRAM traffic. "
+                             "The kernel skips all-air tiles and keeps a chunk of iterations in shared memory, and it is bound by the critical path of the "
+                             "wavefront (latency), not by HBM -- see traffic, and step_roofline for the whole step"},
         "step_roofline": {"alg_bytes_per_step": step_bytes, "achieved": step_bytes / s_per_step / 1e9, "unit": "GB/s",
                           "frac_of_measured": step_bytes / s_per_step / 1e9 / peak, "frac_of_8TBs": step_bytes / s_per_step / 8e12,
                           "formula": "140*P + (96+36*iters)*C  (SURVEY 8d)"},
@@ -889,6 +922,10 @@ def product_arm(args, rank, world, local_rank):
     if world == 1:
         line["eulerian_s1"] = eulerian_bench(local_rank)
     if world == 1 and not args.no_extra_legs and N == BENCH_N:
+        try:
+            line["developed_flow"] = developed_flow(local_rank)
+        except Exception as exc:
+            line["developed_flow"] = {"error": str(exc)[:300]}
         try:
             line["s0_default_tank"] = s0_default_tank(local_rank)
         except Exception as exc:

@@ -145,7 +145,8 @@ int flip_phase_colors(FlipSim* sim);                                            
 /* Reference-order ("exact") mode for parity runs on small scenes: the separation sweeps run in the reference's serial
  * particle order (level-scheduled, flip_fluid.h:203-250 incl. Q1), the P2G adds of every node run in caller order
  * (:398-403, :315-318) and the rest density is the serial running sum of :321-332.  Together with
- * FLIP_SOLVER_LEX_WAVEFRONT a whole flip_step is then bit-identical to FlipFluid::simulate.  Much slower. */
+ * FLIP_SOLVER_LEX_WAVEFRONT a whole flip_step is then bit-identical to FlipFluid::simulate.  Much slower: hundreds of dependent
+ * levels per sweep, and the level schedule is copied to the host every step (a parity mode for small scenes, single GPU only). */
 int flip_set_exact_order(FlipSim* sim, int on);
 /* levels of the last serial-order separation schedule; drifted != 0 if a particle left the 1-cell neighbourhood of its
  * bin during the sweeps (the schedule's validity assumption; never seen on the reference scenes) */

@@ -26,7 +26,11 @@
 
 namespace fg {
 
-constexpr int kTile = 32;        // T: one warp spans a tile row of the skewed square
+#ifndef SOR_TILE
+#define SOR_TILE 32
+#endif
+constexpr int kTile = SOR_TILE;  // T: side of the skewed square (32: one warp spans a tile row).  -DSOR_TILE=64 (1024 threads, one CTA per SM,
+                                 // half the tile waves, twice the diagonal steps per tile) measured 5.18 vs 4.68 ms at S2 and 40.6 vs 40.2 ms at S4
 constexpr int kMaxChunk = 16;    // Kc <= kMaxChunk <= T
 constexpr int kBoxW = kTile + kMaxChunk + 2;  // 50: lanes of one iteration stride by W-1 = 49 (odd, conflict-free) and lanes of
                                              // different iterations packed into one warp collide only for (da,dk) = (2,10), (4,-12) ...
@@ -51,16 +55,14 @@ struct TiledArgs {
 	volatile int* host_status; // ... and in this word of pinned host memory (written by the kernel: no D2H copy on the stream)
 };
 
-// ceil(2^16 / d): floor(n / d) == (n * magic[d]) >> 16 for every n < 1024, d <= 32 (checked exhaustively)
-__constant__ unsigned c_div_magic[33] = {0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554,
-                                         5958,  5462,  5042,  4682,  4370,  4096,  3856,  3641, 3450, 3277, 3121,
-                                         2979,  2850,  2731,  2622,  2521,  2428,  2341,  2260, 2185, 2115, 2048};
+// ceil(2^16 / d): floor(n / d) == (n * magic) >> 16 for every n < 1024, d <= 64 (checked exhaustively)
+__device__ __forceinline__ unsigned div_magic(int d) { return (65536u + (unsigned)d - 1u) / (unsigned)d; }
 
 // The per-step item decode is a multiply-shift by a constant-bank magic number, every operand of a cell is fetched in ONE
 // shared-memory round trip, and the per-solve planes (cell code, drift term) plus the activity map are fetched before the
 // predecessor flags are awaited (r2 A/B on B200, profiles/r2_ab_v2_variants_4096.jsonl: 5.19 -> 4.46 ms at S2, bit-identical).
 template <bool XFAST, bool DRIFT, int KW>  // KW warps per CTA (>= iterations per chunk)
-__global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_kernel(TiledArgs A) {
+__global__ void __launch_bounds__(kTile * KW, (kTile * KW > 512 ? 1 : (KW <= 8 ? 4 : 2))) sor_gs_tiled_kernel(TiledArgs A) {
 	// dynamic shared memory (> 48 KB with the drift term): four float planes and the cell code as a 32-bit word per cell
 	// (a byte plane would put several lanes of a diagonal into one bank)
 	extern __shared__ float smem_tile[];
@@ -71,7 +73,9 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 	float* s_dr = reinterpret_cast<float*>(s_code + kBoxW * kBoxW);  // only touched when DRIFT
 	__shared__ int s_tile;
 	__shared__ int s_ok;
+	__shared__ unsigned s_magic[kTile + 1];
 	const int tid = threadIdx.y * kTile + threadIdx.x;
+	if (tid >= 1 && tid <= kTile) s_magic[tid] = div_magic(tid);
 	const int nthreads = kTile * blockDim.y;
 	const int nf = A.nf, ns = A.ns;
 	for (;;) {
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kTile * KW, (KW <= 8 ? 4 : 2)) sor_gs_tiled_ke
 		for (int t = 0; t < 2 * kTile - 1; t++) {
 			const int alo = max(0, t - (kTile - 1)), cnt = min(kTile - 1, t) - alo + 1;
 			if (tid < cnt * kq) {
-				const int k = (int)(((unsigned)tid * c_div_magic[cnt]) >> 16);  // tid / cnt
+				const int k = (int)(((unsigned)tid * s_magic[cnt]) >> 16);  // tid / cnt
 				const int a = alo + (tid - k * cnt);
 				// F = F0-k+a, S = S0-k+(t-a)  ->  box element (F-FB) + W*(S-SB)
 				const int e = (a - k + A.kc - 1) + kBoxW * (t - a - k + A.kc - 1);
