@@ -48,10 +48,13 @@ inline int num_sms() {
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-// Grid size for grid-stride kernels: whole waves of the SMs, capped by the work available.
+// Grid size for grid-stride kernels: whole waves of the SMs, capped by the work available.  Eight waves rather than one resident
+// wave: the CTAs of a single wave start together and run their memory-stalled and their arithmetic stretches in step, a
+// stream of shorter CTAs interleaves them (separation sweeps at S2: 3.96 -> 3.33 ms, whole step 12.65 -> 11.91 ms; 64 waves: no further gain).
+constexpr int kWavesPerGrid = 8;
 inline unsigned wave_grid(size_t work_items, int threads, int ctas_per_sm = 8) {
 	size_t need = (work_items + threads - 1) / threads;
-	size_t full = (size_t)num_sms() * ctas_per_sm;
+	size_t full = (size_t)num_sms() * ctas_per_sm * kWavesPerGrid;
 	if (need >= full) return (unsigned)full;
 	return (unsigned)(need ? need : 1);
 }

@@ -402,38 +402,42 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 			rn[r] = on ? first[x1 + g.pnx * yi + 1] - ra[r] : 0;
 		}
 		const int n_all = rn[0] + rn[1] + rn[2];
-		// Two passes per chunk of 32 candidates keep the warp converged: pass 1 is the cheap distance test and leaves
-		// a bit mask of overlapping partners; pass 2 runs the sqrt/divide push only for the set bits, in candidate
-		// order (the order of the adds is part of the schedule: oracle orcflip_separate_jacobi).
-		for (int base = 0; base < n_all; base += 32) {
+		// candidate k of the window is slot k + b, b picked by two compares (kept as selects: no branch in the candidate loop)
+		const int n0 = rn[0], n01 = rn[0] + rn[1];
+		const int b0 = ra[0], b1 = ra[1] - n0, b2 = ra[2] - n01;
+		// Two passes keep the warp converged: pass 1 is the cheap distance test and leaves a bit mask of overlapping
+		// partners; pass 2 runs the sqrt/divide push only for the set bits, in candidate order (the order of the adds is
+		// part of the schedule: oracle orcflip_separate_jacobi).  A particle is its own candidate and drops out through
+		// d2 == 0 like any coincident pair (flip_fluid.h:226).
+		auto push = [&](int j) {
+			float2 q = pos_in[j];
+			float dx = q.x - p.x, dy = q.y - p.y;
+			float d2 = dx * dx + dy * dy;
+			float d = sqrtf(d2);
+			float sc = .5f * (min_dist - d) / d;
+			ax -= dx * sc;
+			ay -= dy * sc;
+			if (COLORS) {  // colour diffusion toward the pair mean, flip_fluid.h:239-245
+				float q0 = col_in[3 * (size_t)j], q1 = col_in[3 * (size_t)j + 1], q2 = col_in[3 * (size_t)j + 2];
+				c0 += .001f * ((c0 + q0) / 2.f - c0);
+				c1 += .001f * ((c1 + q1) / 2.f - c1);
+				c2 += .001f * ((c2 + q2) / 2.f - c2);
+			}
+		};
+		for (int base = 0; base < n_all; base += 32) {  // chunks of 32 candidates (one chunk unless the window is crowded)
 			const int n = min(32, n_all - base);
 			unsigned hits = 0;
 			for (int i = 0; i < n; i++) {
 				int k = base + i;
-				int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
-				float2 q = pos_in[j];
+				float2 q = pos_in[k + (k < n0 ? b0 : (k < n01 ? b1 : b2))];
 				float dx = q.x - p.x, dy = q.y - p.y;
 				float d2 = dx * dx + dy * dy;
-				if (j != t && !(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
+				if (!(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
 			}
 			while (hits) {
-				int i = __ffs(hits) - 1;
+				int k = base + __ffs(hits) - 1;
 				hits &= hits - 1;
-				int k = base + i;
-				int j = k < rn[0] ? ra[0] + k : (k < rn[0] + rn[1] ? ra[1] + (k - rn[0]) : ra[2] + (k - rn[0] - rn[1]));
-				float2 q = pos_in[j];
-				float dx = q.x - p.x, dy = q.y - p.y;
-				float d2 = dx * dx + dy * dy;
-				float d = sqrtf(d2);
-				float sc = .5f * (min_dist - d) / d;
-				ax -= dx * sc;
-				ay -= dy * sc;
-				if (COLORS) {  // colour diffusion toward the pair mean, flip_fluid.h:239-245
-					float q0 = col_in[3 * (size_t)j], q1 = col_in[3 * (size_t)j + 1], q2 = col_in[3 * (size_t)j + 2];
-					c0 += .001f * ((c0 + q0) / 2.f - c0);
-					c1 += .001f * ((c1 + q1) / 2.f - c1);
-					c2 += .001f * ((c2 + q2) / 2.f - c2);
-				}
+				push(k + (k < n0 ? b0 : (k < n01 ? b1 : b2)));
 			}
 		}
 		float2 pn = make_float2(ax, ay);
