@@ -401,10 +401,6 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 			ra[r] = on ? first[x0 + g.pnx * yi] : 0;
 			rn[r] = on ? first[x1 + g.pnx * yi + 1] - ra[r] : 0;
 		}
-		const int n_all = rn[0] + rn[1] + rn[2];
-		// candidate k of the window is slot k + b, b picked by two compares (kept as selects: no branch in the candidate loop)
-		const int n0 = rn[0], n01 = rn[0] + rn[1];
-		const int b0 = ra[0], b1 = ra[1] - n0, b2 = ra[2] - n01;
 		// Two passes keep the warp converged: pass 1 is the cheap distance test and leaves a bit mask of overlapping
 		// partners; pass 2 runs the sqrt/divide push only for the set bits, in candidate order (the order of the adds is
 		// part of the schedule: oracle orcflip_separate_jacobi).  A particle is its own candidate and drops out through
@@ -424,20 +420,47 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 				c2 += .001f * ((c2 + q2) / 2.f - c2);
 			}
 		};
-		for (int base = 0; base < n_all; base += 32) {  // chunks of 32 candidates (one chunk unless the window is crowded)
-			const int n = min(32, n_all - base);
-			unsigned hits = 0;
-			for (int i = 0; i < n; i++) {
-				int k = base + i;
-				float2 q = pos_in[k + (k < n0 ? b0 : (k < n01 ? b1 : b2))];
-				float dx = q.x - p.x, dy = q.y - p.y;
-				float d2 = dx * dx + dy * dy;
-				if (!(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
+		if (max(rn[0], max(rn[1], rn[2])) <= 32) {
+			// the usual window: each row is walked with a plain pointer (four loads in flight), its hits pushed before the next row
+#pragma unroll
+			for (int r = 0; r < 3; r++) {
+				const float2* __restrict__ row = pos_in + ra[r];
+				unsigned hits = 0;
+#pragma unroll 4
+				for (int i = 0; i < rn[r]; i++) {
+					float2 q = row[i];
+					float dx = q.x - p.x, dy = q.y - p.y;
+					float d2 = dx * dx + dy * dy;
+					hits |= (unsigned)!(d2 > min_dist_sq || d2 == 0.f) << i;
+				}
+				while (hits) {
+					int i = __ffs(hits) - 1;
+					hits &= hits - 1;
+					push(ra[r] + i);
+				}
 			}
-			while (hits) {
-				int k = base + __ffs(hits) - 1;
-				hits &= hits - 1;
-				push(k + (k < n0 ? b0 : (k < n01 ? b1 : b2)));
+		} else {
+			// crowded window: candidates numbered through the three rows, chunks of 32; candidate k is slot k + b, b picked by
+			// two compares (kept as selects: no branch in the candidate loop)
+			const int n_all = rn[0] + rn[1] + rn[2];
+			const int n0 = rn[0], n01 = rn[0] + rn[1];
+			const int b0 = ra[0], b1 = ra[1] - n0, b2 = ra[2] - n01;
+#pragma unroll 1
+			for (int base = 0; base < n_all; base += 32) {
+				const int n = min(32, n_all - base);
+				unsigned hits = 0;
+				for (int i = 0; i < n; i++) {
+					int k = base + i;
+					float2 q = pos_in[k + (k < n0 ? b0 : (k < n01 ? b1 : b2))];
+					float dx = q.x - p.x, dy = q.y - p.y;
+					float d2 = dx * dx + dy * dy;
+					if (!(d2 > min_dist_sq || d2 == 0.f)) hits |= 1u << i;
+				}
+				while (hits) {
+					int k = base + __ffs(hits) - 1;
+					hits &= hits - 1;
+					push(k + (k < n0 ? b0 : (k < n01 ? b1 : b2)));
+				}
 			}
 		}
 		float2 pn = make_float2(ax, ay);
@@ -639,7 +662,9 @@ __global__ void __launch_bounds__(kThreads) k_g2p(Geo g, const float2* __restric
                                                   const float* __restrict__ u, const float* __restrict__ v,
                                                   const float* __restrict__ prev_u, const float* __restrict__ prev_v,
                                                   const int* __restrict__ cell_type, float flip_ratio,
-                                                  const int* __restrict__ orig, float2* __restrict__ staging) {
+                                                  const int* __restrict__ orig, float2* __restrict__ staging,
+                                                  int* __restrict__ vmax_bits) {
+	float vmax = 0.f;  // sharded steps: largest |v_y| leaving this step, which sizes the next step's ghost band (k_shard_band)
 	for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.np; t += gridDim.x * blockDim.x) {
 		float2 p = pos[t];
 		if (STAGE) staging[orig[t]] = p;
@@ -682,6 +707,11 @@ __global__ void __launch_bounds__(kThreads) k_g2p(Geo g, const float2* __restric
 			}
 		}
 		vel[t] = pv;
+		vmax = fmaxf(vmax, fabsf(pv.y));
+	}
+	if (vmax_bits) {
+		const int mi = warp_max(__float_as_int(vmax));
+		if ((threadIdx.x & 31) == 0 && mi > 0) atomicMax(vmax_bits, mi);
 	}
 }
 
@@ -767,9 +797,10 @@ __global__ void __launch_bounds__(kThreads) k_shard_vmax(int np, const float2* _
 // most (vmax + |g| dt) dt by integration, then up to one overlap (2.2r hash cell + r push) per separation sweep -- each
 // Jacobi sweep also widens the dependency cone by one hash cell -- and its bilinear stencil reaches one more cell; +2 rows
 // of slack.  The same value on every rank (vmax is all-reduced); the host refuses a band wider than the thinnest slab.
-__global__ void k_shard_band(const int* __restrict__ vmax_bits, float dt, float gravity, float h, float r, int sep_iters, int* __restrict__ band) {
+__global__ void k_shard_band(int* __restrict__ vmax_bits, float dt, float gravity, float h, float r, int sep_iters, int* __restrict__ band) {
 	if (threadIdx.x != 0) return;
 	float v = __int_as_float(*vmax_bits) + fabsf(gravity) * dt;
+	*vmax_bits = 0;  // consumed: the G2P of this step accumulates the next one
 	float reach = v * dt / h + (float)sep_iters * (3.2f * r) / h;
 	int b = (int)ceilf(reach) + 1 + 2;
 	*band = max(b, 6);
@@ -780,56 +811,90 @@ __global__ void k_shard_band(const int* __restrict__ vmax_bits, float dt, float 
 // crossed the boundary was a ghost on its new owner, whose copy -- integrated, separated and G2P'd inside that rank's
 // valid rows -- is the one that survives.  (The band below is wide enough that every such particle WAS a ghost there.)
 // Kept particles within `band` rows of a boundary are copied to that neighbour as this step's ghosts.
-__global__ void __launch_bounds__(kThreads) k_shard_classify(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
-                                                             const float2* __restrict__ pos, const float2* __restrict__ vel,
-                                                             const int* __restrict__ id, ShardPack keep, ShardPack down, ShardPack up,
-                                                             int* __restrict__ counters /* [0] keep [1] down [2] up */, int cap_send, int exchange) {
-	// Slots are claimed per CTA: one atomic per counter and block instead of one per warp (64 M particles -> 2 M same-address
-	// atomics serialise at the L2: 2.9 ms per step at S2 before this, profiles/r2_sharded.md).  Any order of the kept particles
-	// will do: the counting sort that follows orders by (hash cell, global id).
-	const int band = exchange ? *band_p : 0;
-	__shared__ int s_cnt[3], s_base[3];
-	const int lane = threadIdx.x & 31;
-	for (int t0 = blockIdx.x * blockDim.x; t0 < g.np; t0 += gridDim.x * blockDim.x) {
-		const int t = t0 + threadIdx.x;
-		if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
-		__syncthreads();
-		float2 p = make_float2(0.f, 0.f), v = make_float2(0.f, 0.f);
-		int gid = 0;
-		bool own = false, go_down = false, go_up = false;
-		if (t < g.np) {
-			p = pos[t];
-			const int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
-			own = row >= j0 && row < j1;
-			if (own) {
-				v = vel[t]; gid = id[t];
-				go_down = exchange && has_down && row < j0 + band;
-				go_up = exchange && has_up && row >= j1 - band;
-			}
-		}
-		// warp-level ranks, then one shared-memory add per warp and class
-		int slot[3];
-		const bool flag[3] = {own, go_down, go_up};
+// Ownership is by position: a particle belongs to the rank whose slab holds its cell row; owned particles within `band` rows of
+// a slab boundary also go to that neighbour (as ghosts, or as migrants it now owns).  The three classes are compacted in
+// two passes over 256-particle chunks -- count, one scan of the chunk counts, place -- so the kept particles stay in the order
+// they had (hash-cell order from the last step): the counting sort that follows then fills and reorders with the memory
+// locality of the one-GPU step.  (Slots claimed with atomics in arrival order scrambled the chunks: k_fill 0.35 -> 0.9-1.05 ms
+// at S2, k_fixup_cells 0.49 -> 0.63 ms, profiles/r2_sharded.md.)
+struct ShardClass { bool own, go_down, go_up; };
+__device__ __forceinline__ ShardClass shard_class(const Geo& g, float2 p, int j0, int j1, int band, int has_down, int has_up) {
+	const int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
+	ShardClass c;
+	c.own = row >= j0 && row < j1;
+	c.go_down = c.own && has_down && row < j0 + band;
+	c.go_up = c.own && has_up && row >= j1 - band;
+	return c;
+}
+// One WARP per chunk of kShardChunk particles (no block barriers, the chunk's loads in flight together).
+constexpr int kShardChunk = 256;
+__global__ void __launch_bounds__(kThreads) k_shard_count(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
+                                                          const float2* __restrict__ pos, int n_chunks, int* __restrict__ chunk_cnt /* [3][n_chunks] */) {
+	const int band = band_p ? *band_p : 0;
+	const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+	for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
+		int n0 = 0, n1 = 0, n2 = 0;
 #pragma unroll
-		for (int c = 0; c < 3; c++) {
-			const unsigned m = __ballot_sync(0xffffffffu, flag[c]);
-			int base = 0;
-			if (lane == 0 && m) base = atomicAdd(&s_cnt[c], __popc(m));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			slot[c] = base + __popc(m & ((1u << lane) - 1u));
+		for (int i = 0; i < kShardChunk / 32; i++) {
+			const int t = chunk * kShardChunk + i * 32 + lane;
+			ShardClass c{false, false, false};
+			if (t < g.np) c = shard_class(g, pos[t], j0, j1, band, has_down, has_up);
+			n0 += __popc(__ballot_sync(0xffffffffu, c.own));
+			n1 += __popc(__ballot_sync(0xffffffffu, c.go_down));
+			n2 += __popc(__ballot_sync(0xffffffffu, c.go_up));
 		}
-		__syncthreads();
-		if (threadIdx.x < 3) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(counters + threadIdx.x, s_cnt[threadIdx.x]) : 0;
-		__syncthreads();
-		if (own) { const int k = s_base[0] + slot[0]; keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid; }
-		if (go_down) { const int m = s_base[1] + slot[1]; if (m < cap_send) { down.pos[m] = p; down.vel[m] = v; down.id[m] = gid; } }
-		if (go_up) { const int m = s_base[2] + slot[2]; if (m < cap_send) { up.pos[m] = p; up.vel[m] = v; up.id[m] = gid; } }
-		__syncthreads();
+		if (lane == 0) { chunk_cnt[chunk] = n0; chunk_cnt[n_chunks + chunk] = n1; chunk_cnt[2 * n_chunks + chunk] = n2; }
 	}
 }
-
-// capacity check of the exchange, on the device: [7] = 1 if this rank cannot send or hold what the step needs.  The flag is
-// all-reduced (max) before the host looks at it, so every rank takes the error exit together and none stays blocked in NCCL.
+// chunk_incl: inclusive running sum over the three count rows laid end to end (running_sum)
+__global__ void __launch_bounds__(kThreads) k_shard_place(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
+                                                          const float2* __restrict__ pos, const float2* __restrict__ vel, const int* __restrict__ id,
+                                                          ShardPack keep, ShardPack down, ShardPack up, int n_chunks,
+                                                          const int* __restrict__ chunk_cnt, const int* __restrict__ chunk_incl, int cap_send,
+                                                          int integrate, float dt, float gravity, int* __restrict__ keys, int* __restrict__ count,
+                                                          int* __restrict__ counters) {
+	const int band = band_p ? *band_p : 0;
+	const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+	const unsigned lt = (1u << lane) - 1u;
+	const int tot0 = chunk_incl[n_chunks - 1], tot1 = chunk_incl[2 * n_chunks - 1], tot2 = chunk_incl[3 * n_chunks - 1];
+	if (blockIdx.x == 0 && threadIdx.x == 0) { counters[0] = tot0; counters[1] = tot1 - tot0; counters[2] = tot2 - tot1; }
+	for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
+		int at0 = chunk_incl[chunk] - chunk_cnt[chunk];
+		int at1 = chunk_incl[n_chunks + chunk] - chunk_cnt[n_chunks + chunk] - tot0;
+		int at2 = chunk_incl[2 * n_chunks + chunk] - chunk_cnt[2 * n_chunks + chunk] - tot1;
+#pragma unroll 4
+		for (int i = 0; i < kShardChunk / 32; i++) {
+			const int t = chunk * kShardChunk + i * 32 + lane;
+			float2 p = make_float2(0.f, 0.f), v = make_float2(0.f, 0.f);
+			int gid = 0;
+			ShardClass c{false, false, false};
+			if (t < g.np) {
+				p = pos[t];
+				c = shard_class(g, p, j0, j1, band, has_down, has_up);
+				if (c.own) { v = vel[t]; gid = id[t]; }
+			}
+			const unsigned m0 = __ballot_sync(0xffffffffu, c.own), m1 = __ballot_sync(0xffffffffu, c.go_down), m2 = __ballot_sync(0xffffffffu, c.go_up);
+			// boundary copies go out as they are: their receiver integrates them
+			if (c.go_down) { const int k = at1 + __popc(m1 & lt); if (k < cap_send) { down.pos[k] = p; down.vel[k] = v; down.id[k] = gid; } }
+			if (c.go_up) { const int k = at2 + __popc(m2 & lt); if (k < cap_send) { up.pos[k] = p; up.vel[k] = v; up.id[k] = gid; } }
+			if (c.own) {
+				const int k = at0 + __popc(m0 & lt);
+				if (integrate) {
+					// the kept copy leaves integrated and keyed for the sort (the arithmetic of k_integrate_bin<true, true>): one pass
+					// over the owned particles less per step
+					v.y += gravity * dt;
+					p.x += v.x * dt;
+					p.y += v.y * dt;
+					const int key = hash_cell(g, p.x, p.y);
+					keys[k] = key;
+					atomicAdd(count + key, 1);
+				}
+				keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
+			}
+			at0 += __popc(m0); at1 += __popc(m1); at2 += __popc(m2);
+		}
+	}
+}
 __global__ void k_shard_check(int* __restrict__ c, int cap_send, int max_particles) {
 	if (threadIdx.x != 0) return;
 	c[7] = (c[1] > cap_send || c[2] > cap_send || (long long)c[0] + c[3] + c[4] > (long long)max_particles) ? 1 : 0;
@@ -1043,7 +1108,10 @@ struct FlipSim {
 	float2 *send_pos[2] = {nullptr, nullptr}, *send_vel[2] = {nullptr, nullptr};
 	int* send_id[2] = {nullptr, nullptr};
 	int cap_send = 0;
-	int* d_counters = nullptr;   // [0] keep [1] down [2] up [3] from-down [4] from-up [5] vmax bits [6] ghost band (rows)
+	int* d_chunk = nullptr;      // [3][chunks of 256 particles] per-chunk counts of the kept / down / up classes, then (at chunk_stride) their running sum
+	size_t chunk_stride = 0;
+	int* d_counters = nullptr;   // [0] keep [1] down [2] up [3] from-down [4] from-up [6] ghost band (rows) [7] error flag [8] vmax bits
+	bool vmax_valid = false;     // d_counters[8] holds the largest |v_y| of the current particle state (left by the G2P of a sharded step)
 	int global_particles = 0;
 	int* h_counters = nullptr;   // pinned mirror
 	int n_owned = 0;
@@ -1466,12 +1534,13 @@ int g2p(FlipSim* f, float flip_ratio, bool stage = false) {
 	if (stage && !f->identity) {
 		int b = 0;
 		FG_TRY(next_staging(f, &b));
-		k_g2p<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio, f->orig[c], f->staging[b]);
+		k_g2p<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio, f->orig[c], f->staging[b], nullptr);
 		f->lc.n++;
 		FG_CUDA(cudaGetLastError());
 		return staged(f, b);
 	}
-	k_g2p<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio, nullptr, nullptr);
+	k_g2p<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->pos[c], f->vel[c], f->u, f->v, f->prev_u, f->prev_v, f->cell_type, flip_ratio, nullptr, nullptr, f->sharded ? f->d_counters + 8 : nullptr);
+	f->vmax_valid = f->sharded;
 	f->lc.n++;
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
@@ -1493,7 +1562,9 @@ int shard_rest_latch(FlipSim* f) {
 }
 
 // swap `rows` rows at both slab boundaries: my outermost own rows go into the neighbour's halo and vice versa.
-// Arrays keep the global size, so a row sits at the same offset on every rank.
+// Arrays keep the global size, so a row sits at the same offset on every rank.  (One send/recv pair per field: packing the
+// fields into one message per neighbour was measured and changed nothing -- 12.9 vs 13.0 ms per step at 2 GPUs; what the
+// phase table shows around an exchange is the wait for the slower rank, not the transfer.)
 int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows) {
 	if (f->nranks == 1) return FLIPGPU_OK;
 	const size_t nx = f->d.f_num_x, blk = nx * rows;
@@ -1515,23 +1586,46 @@ int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows)
 	return FLIPGPU_OK;
 }
 
+// Stable compaction of buffer `cur` into buffer `1 - cur`: owned particles (optionally integrated + keyed, see k_shard_place),
+// and with `exchange` the boundary copies for both neighbours into the send buffers.  Leaves the three counts in d_counters[0..2].
+int shard_compact(FlipSim* f, bool exchange, bool integrate, float dt, float gravity) {
+	Geo g = geo(f);
+	if (g.np <= 0) return FLIPGPU_OK;   // (the counters were cleared by the caller)
+	const int c = f->cur, n = 1 - c;
+	const bool has_up = exchange && f->rank + 1 < f->nranks, has_down = exchange && f->rank > 0;
+	const int n_chunks = (int)cdiv((size_t)g.np, (size_t)kShardChunk);
+	const int* band = exchange ? f->d_counters + 6 : nullptr;
+	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
+	const unsigned grid = wave_grid((size_t)n_chunks * 32, kThreads);
+	int* incl = f->d_chunk + f->chunk_stride;
+	k_shard_count<<<grid, kThreads, 0, f->st>>>(g, f->j0, f->j1, band, has_down, has_up, f->pos[c], n_chunks, f->d_chunk);
+	running_sum(f, f->d_chunk, 3 * n_chunks, incl);
+	k_shard_place<<<grid, kThreads, 0, f->st>>>(g, f->j0, f->j1, band, has_down, has_up, f->pos[c], f->vel[c], f->orig[c], keep, down, up, n_chunks, f->d_chunk,
+	                                            incl, f->cap_send, integrate ? 1 : 0, dt, gravity, f->keys, f->count, f->d_counters);
+	f->lc.n += 2;
+	FG_CUDA(cudaGetLastError());
+	return FLIPGPU_OK;
+}
+
 // keep what this rank owns (by position), refresh the ghosts from both neighbours
 int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters) {
 	Geo g = geo(f);
 	const int c = f->cur, n = 1 - c;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
+	FG_TRY(positions_will_change(f));
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
-	// ghost band for this step from the fastest owned particle anywhere (device-side: no host round trip)
-	if (g.np > 0) { k_shard_vmax<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->vel[c], f->d_counters + 5); f->lc.n++; }
-	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 5, f->d_counters + 5, 1, ncclInt, ncclMax, f->comm, f->st));
-	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 5, dt, gravity, f->d.h, f->d.particle_radius, sep_iters, f->d_counters + 6);
-	f->lc.n++;
-	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
-	if (g.np > 0) {
-		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, f->d_counters + 6, has_down, has_up, f->pos[c], f->vel[c], f->orig[c],
-		                                                    keep, down, up, f->d_counters, f->cap_send, 1);
-		f->lc.n++;
+	FG_CUDA(cudaMemsetAsync(f->count + (size_t)g.pnx * g.hy0, 0, (size_t)g.pnx * (g.hy1 - g.hy0) * 4, f->st));   // this step's hash histogram
+	// ghost band for this step from the fastest particle anywhere (device-side: no host round trip).  The G2P of the last
+	// step left the maximum behind; after an upload (or before the first step) it is taken here.
+	if (!f->vmax_valid) {
+		FG_CUDA(cudaMemsetAsync(f->d_counters + 8, 0, sizeof(int), f->st));
+		if (g.np > 0) { k_shard_vmax<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->vel[c], f->d_counters + 8); f->lc.n++; }
 	}
+	f->vmax_valid = false;
+	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 8, f->d_counters + 8, 1, ncclInt, ncclMax, f->comm, f->st));
+	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 8, dt, gravity, f->d.h, f->d.particle_radius, sep_iters, f->d_counters + 6);
+	f->lc.n++;
+	FG_TRY(shard_compact(f, true, true, dt, gravity));
 	// tell each neighbour how many particles are coming (device-to-device ints), then read the counters once
 	if (f->nranks > 1) {
 		FG_NCCL(g_nccl.GroupStart());
@@ -1585,10 +1679,17 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters)
 		FG_NCCL(g_nccl.GroupEnd());
 		f->exchanges++;
 	}
+	const int n_recv = from_down + from_up;
+	if (n_recv > 0) {  // the received ghosts and migrants: integrate + key + histogram like the kept ones
+		Geo gt = g;
+		gt.np = n_recv;
+		k_integrate_bin<true, true><<<wave_grid((size_t)n_recv, kThreads), kThreads, 0, f->st>>>(gt, f->pos[n] + n_keep, f->vel[n] + n_keep, dt, gravity, f->keys + n_keep, f->count);
+		f->lc.n++;
+	}
 	FG_CUDA(cudaGetLastError());
 	f->cur = n;
 	f->n_owned = n_keep;
-	f->d.num_particles = n_keep + from_down + from_up;
+	f->d.num_particles = n_keep + n_recv;
 	f->identity = false;
 	f->bins_valid = false;
 	return FLIPGPU_OK;
@@ -1639,11 +1740,11 @@ int shard_step(FlipSim* f, const FlipStepParams* sp) {
 	// integrate_bin, post-P2G halo rows under p2g, post-solve halo rows under g2p
 	if (f->timings_on) collect_slot(f, f->ev_slot);
 	phase_mark(f, FLIP_PH_INTEGRATE_BIN);
-	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity, sp->separate_particles ? sp->num_particle_iters : 0));              // migrants change owner, ghosts are refreshed
+	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity, sp->separate_particles ? sp->num_particle_iters : 0));              // migrants change owner, ghosts are refreshed; F1 + sort keys
 	// (the exchange synchronised the stream, so the previous step -- and its copy of the rest density -- is complete on
 	// every rank: all ranks take the same branch below and issue the same NCCL calls)
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
-	FG_TRY(integrate_and_bin(f, true, true, sp->dt, sp->gravity));         // owned + ghosts
+	FG_TRY(bin_from_histogram(f));                                         // owned + ghosts, integrated and keyed by the exchange
 	phase_mark(f, FLIP_PH_SEPARATE);
 	// as in the one-GPU step, the last sweep runs the collision / marking pass itself (identical results)
 	const bool fused = sp->separate_particles && sp->num_particle_iters >= 1 && f->d.num_particles > 0;
@@ -1826,6 +1927,7 @@ int flip_destroy(FlipSim* f) {
 	for (auto& G : f->graphs) if (G.exec) cudaGraphExecDestroy(G.exec);
 	if (f->comm) g_nccl.CommDestroy(f->comm);
 	for (int k = 0; k < 2; k++) { cudaFree(f->send_pos[k]); cudaFree(f->send_vel[k]); cudaFree(f->send_id[k]); }
+	cudaFree(f->d_chunk);
 	cudaFree(f->d_counters);
 	cudaFree(f->lvl[0]); cudaFree(f->lvl[1]); cudaFree(f->d_flags);
 	if (f->h_counters) cudaFreeHost(f->h_counters);
@@ -2131,13 +2233,16 @@ int flip_create_sharded_rows(const FlipParams* pr, int global_particles, int ran
 	f->hy0 = std::max((int)((float)f->gy0 * f->d.h * f->d.p_inv_spacing) - 1, 0);
 	f->hy1 = std::min((int)((float)f->gy1 * f->d.h * f->d.p_inv_spacing) + 2, f->d.p_num_y);
 	f->cap_send = std::max(f->d.max_particles / 2, 1024);
+	f->chunk_stride = (3 * (size_t)cdiv((size_t)std::max(f->d.max_particles, 1), (size_t)kShardChunk) + 7) & ~(size_t)3;
+	FG_CUDA(cudaMalloc(&f->d_chunk, 2 * f->chunk_stride * sizeof(int)));
 	f->global_particles = global_particles;
 	for (int k = 0; k < 2; k++) {
 		FG_CUDA(cudaMalloc(&f->send_pos[k], (size_t)f->cap_send * sizeof(float2)));
 		FG_CUDA(cudaMalloc(&f->send_vel[k], (size_t)f->cap_send * sizeof(float2)));
 		FG_CUDA(cudaMalloc(&f->send_id[k], (size_t)f->cap_send * 4));
 	}
-	FG_CUDA(cudaMalloc(&f->d_counters, 8 * sizeof(int)));
+	FG_CUDA(cudaMalloc(&f->d_counters, 12 * sizeof(int)));
+	FG_CUDA(cudaMemset(f->d_counters, 0, 12 * sizeof(int)));
 	FG_CUDA(cudaMallocHost(&f->h_counters, 8 * sizeof(int)));
 	f->d.num_particles = 0;
 	f->identity = false;
@@ -2174,7 +2279,7 @@ int flip_upload_particles(FlipSim* f, const float* pos, const float* vel, const 
 		FG_CUDA(cudaMemcpyAsync(f->orig[c], ids, (size_t)n * 4, cudaMemcpyHostToDevice, f->st));
 	}
 	FG_CUDA(cudaStreamSynchronize(f->st));
-	f->d.num_particles = n; f->n_owned = n; f->bins_valid = false; f->identity = false;
+	f->d.num_particles = n; f->n_owned = n; f->bins_valid = false; f->identity = false; f->vmax_valid = false;
 	return FLIPGPU_OK;
 }
 
@@ -2186,12 +2291,7 @@ int flip_readback_particles(FlipSim* f, float* pos, float* vel, int* ids, int ca
 	Geo g = geo(f);
 	const int c = f->cur, n = 1 - c;
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
-	ShardPack keep{f->pos[n], f->vel[n], f->orig[n]}, none{nullptr, nullptr, nullptr};
-	if (g.np > 0) {
-		k_shard_classify<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, nullptr, 0, 0, f->pos[c], f->vel[c], f->orig[c], keep, none, none,
-		                                                    f->d_counters, 0, 0);
-		f->lc.n++;
-	}
+	FG_TRY(shard_compact(f, false, false, 0.f, 0.f));
 	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	const int k = f->h_counters[0];
