@@ -246,12 +246,24 @@ __global__ void __launch_bounds__(kThreads) k_fill(int np, const int* __restrict
 }
 // ... and each cell's segment is then put into the reference's order: DESCENDING caller index (Q7),
 // which is what the serial decrement-on-fill of :196-197 produces.  Deterministic and bit-exact.
+// Segments longer than kCrowd (particles piled up against a wall: hundreds per cell in a developed flow) are not sorted by
+// their one thread -- an insertion sort of 535 entries through global memory kept the whole kernel waiting for 1.5 ms at S2 --
+// but queued for k_fixup_crowded, which ranks a segment with a whole CTA.  A full queue falls back to the in-thread sort.
+constexpr int kCrowd = 16, kCrowdMax = 4096, kCrowdCap = 1 << 20;
+struct CrowdQueue { int* list; int* count; };
+__device__ __forceinline__ bool crowd_push(const CrowdQueue& q, int c) {
+	const int k = atomicAdd(q.count, 1);
+	if (k >= kCrowdCap) return false;
+	q.list[k] = c;
+	return true;
+}
 __global__ void __launch_bounds__(kThreads) k_fixup_cells(int n_cells, const int* __restrict__ count,
                                                           const int* __restrict__ first, int* __restrict__ src,
-                                                          int* __restrict__ ids) {
+                                                          int* __restrict__ ids, CrowdQueue crowd) {
 	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
 		int n = count[c];
 		if (n < 2) continue;
+		if (n > kCrowd && crowd_push(crowd, c)) continue;
 		int b = first[c];
 		// (id, src) packed into one 64-bit key, negated: ascending order of the key == descending id (ids are unique)
 		if (n == 2) {
@@ -292,6 +304,47 @@ __global__ void __launch_bounds__(kThreads) k_fixup_cells(int n_cells, const int
 			ids[b + j + 1] = id;
 			src[b + j + 1] = sv;
 		}
+	}
+}
+
+// The queued segments, one CTA each: rank sort in shared memory (ids and slot numbers are unique, so the rank of an entry is the
+// number of entries that precede it in the order).  CELLS: (id, src) pairs by DESCENDING id (k_fixup_cells); else slot numbers
+// ascending (k_fixup_grid).  Same result as the in-thread sorts.  Longer than kCrowdMax: thread 0 sorts by insertion.
+template <bool CELLS>
+__global__ void __launch_bounds__(256) k_fixup_crowded(CrowdQueue crowd, const int* __restrict__ count, const int* __restrict__ first,
+                                                       int* __restrict__ a /* src (CELLS) or the slot list */, int* __restrict__ ids) {
+	__shared__ int s_key[kCrowdMax];
+	__shared__ int s_val[CELLS ? kCrowdMax : 1];
+	const int total = min(*crowd.count, kCrowdCap);
+	for (int i = blockIdx.x; i < total; i += gridDim.x) {
+		const int c = crowd.list[i], n = count[c], b = first[c];
+		if (n > kCrowdMax) {
+			if (threadIdx.x == 0) {
+				for (int k = 1; k < n; k++) {
+					const int key = CELLS ? ids[b + k] : a[b + k], val = CELLS ? a[b + k] : 0;
+					int j = k - 1;
+					while (j >= 0 && (CELLS ? ids[b + j] < key : a[b + j] > key)) {
+						if (CELLS) { ids[b + j + 1] = ids[b + j]; }
+						a[b + j + 1] = a[b + j];
+						j--;
+					}
+					if (CELLS) { ids[b + j + 1] = key; a[b + j + 1] = val; } else a[b + j + 1] = key;
+				}
+			}
+			continue;
+		}
+		for (int t = threadIdx.x; t < n; t += blockDim.x) {
+			s_key[t] = CELLS ? ids[b + t] : a[b + t];
+			if (CELLS) s_val[t] = a[b + t];
+		}
+		__syncthreads();
+		for (int t = threadIdx.x; t < n; t += blockDim.x) {
+			const int key = s_key[t];
+			int r = 0;
+			for (int j = 0; j < n; j++) r += CELLS ? (s_key[j] > key) : (s_key[j] < key);
+			if (CELLS) { ids[b + r] = key; a[b + r] = s_val[t]; } else a[b + r] = key;
+		}
+		__syncthreads();
 	}
 }
 
@@ -534,10 +587,11 @@ __global__ void __launch_bounds__(kThreads) k_fill_grid(int np, const int* __res
 }
 // ... then every cell's list is sorted by slot number, which fixes the order of the float adds of the gather
 __global__ void __launch_bounds__(kThreads) k_fixup_grid(int n_cells, const int* __restrict__ gcount,
-                                                         const int* __restrict__ gfirst, int* __restrict__ gidx) {
+                                                         const int* __restrict__ gfirst, int* __restrict__ gidx, CrowdQueue crowd) {
 	for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
 		int n = gcount[c];
 		if (n < 2) continue;
+		if (n > kCrowd && crowd_push(crowd, c)) continue;
 		int b = gfirst[c];
 		if (n <= 16) {
 			int v[16];
@@ -1080,6 +1134,8 @@ struct FlipSim {
 	int* orig[2] = {nullptr, nullptr};   // caller index per slot; orig[cur] doubles as cell_particle_ids
 	int cur = 0;
 	int *keys = nullptr, *src = nullptr, *count = nullptr, *first = nullptr, *tile_sum = nullptr;
+	int* crowd_list = nullptr;   // crowded hash cells / grid cells of this step's sorts (k_fixup_crowded); [kCrowdCap] + 1 count word
+
 	int *gcount = nullptr, *gfirst = nullptr;  // particles per stencil base cell (P2G gather lists; keys/src are reused for them)
 	float* d_rest = nullptr;   // device scalar particle_rest_density
 	float* d_partials = nullptr;
@@ -1270,6 +1326,7 @@ void collect_timings(FlipSim* f) {
 	for (int s = 0; s < FlipSim::kEvRing; s++) collect_slot(f, s);
 }
 
+inline unsigned crowd_grid() { return (unsigned)num_sms() * 4; }
 // inclusive running sum of count[0..n) into first[0..n), first[n] = total (flip_fluid.h:180-186)
 void running_sum(FlipSim* f, const int* count, int n, int* first) {
 	int tiles = (int)cdiv((size_t)n, kScanTile);
@@ -1288,7 +1345,11 @@ int bin_from_histogram(FlipSim* f, bool integrate = false, float dt = 0.f, float
 	int c = f->cur, n = 1 - c;
 	if (np > 0) {
 		k_fill<<<pgrid(f), kThreads, 0, f->st>>>(np, f->keys, f->orig[c], f->first, f->src, f->orig[n]);
-		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count + hoff, f->first + hoff, f->src, f->orig[n]);
+		const CrowdQueue crowd{f->crowd_list, f->crowd_list + kCrowdCap};
+		FG_CUDA(cudaMemsetAsync(crowd.count, 0, 4, f->st));
+		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count + hoff, f->first + hoff, f->src, f->orig[n], crowd);
+		k_fixup_crowded<true><<<crowd_grid(), 256, 0, f->st>>>(crowd, f->count + hoff, f->first + hoff, f->src, f->orig[n]);
+		f->lc.n++;
 		if (f->col[0]) {
 			if (integrate) k_reorder<true, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], dt, gravity);
 			else k_reorder<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], 0.f, 0.f);
@@ -1453,7 +1514,13 @@ int collide_mark(FlipSim* f, bool collide, bool mark, float ox, float oy, float 
 		if (g.np > 0) {
 			k_fill_grid<<<pgrid(f), kThreads, 0, f->st>>>(g.np, f->keys, f->gfirst, f->src);
 			if (f->exact_order) k_fixup_grid_by_id<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src, f->orig[c]);
-			else k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src);
+			else {
+				const CrowdQueue crowd{f->crowd_list, f->crowd_list + kCrowdCap};
+				FG_CUDA(cudaMemsetAsync(crowd.count, 0, 4, f->st));
+				k_fixup_grid<<<wave_grid(C, kThreads), kThreads, 0, f->st>>>(C, f->gcount + goff, f->gfirst + goff, f->src, crowd);
+				k_fixup_crowded<false><<<crowd_grid(), 256, 0, f->st>>>(crowd, f->gcount + goff, f->gfirst + goff, f->src, nullptr);
+				f->lc.n++;
+			}
 			f->lc.n += 2;
 		}
 	}
@@ -1920,6 +1987,7 @@ int flip_create(const FlipParams* pr, FlipSim** out) {
 	FG_CUDA(cudaMemsetAsync(f->first, 0, (H + 1) * 4, f->st));
 	FG_CUDA(cudaMemsetAsync(f->src, 0, M * 4, f->st));
 	FG_CUDA(cudaMalloc(&f->tile_sum, (size_t)(cdiv(std::max(H, C), kScanTile) + 1) * 4));
+	FG_CUDA(cudaMalloc(&f->crowd_list, ((size_t)kCrowdCap + 1) * 4));
 	FG_CUDA(cudaMalloc(&f->d_rest, 4));
 	FG_CUDA(cudaMemsetAsync(f->d_rest, 0, 4, f->st));
 	FG_CUDA(cudaMalloc(&f->d_partials, (3 * kPartials + 8) * 4));
@@ -1942,7 +2010,7 @@ int flip_destroy(FlipSim* f) {
 	cudaStreamSynchronize(f->st);
 	void* ptrs[] = {f->u, f->v, f->prev_u, f->prev_v, f->p, f->s, f->dens, f->cell_type, f->cell_color, f->pos[0], f->pos[1],
 	                f->vel[0], f->vel[1], f->col[0], f->col[1], f->orig[0], f->orig[1], f->keys, f->src, f->gcount, f->gfirst, f->count, f->u_alt, f->v_alt, f->p_alt,
-	                f->first, f->tile_sum, f->d_rest, f->d_partials};
+	                f->first, f->tile_sum, f->crowd_list, f->d_rest, f->d_partials};
 	for (void* p : ptrs) if (p) cudaFree(p);
 	for (auto& G : f->graphs) if (G.exec) cudaGraphExecDestroy(G.exec);
 	if (f->comm) g_nccl.CommDestroy(f->comm);

@@ -395,12 +395,14 @@ def test_empty_and_single_particle():
 def test_particles_outside_domain_and_crowded_cell():
     """Clamped hash keys (flip_fluid.h:174-175), many particles in one cell, positions outside the tank."""
     rng = np.random.default_rng(7)
-    o = co.FlipOracle(1000.0, 2.0, 1.5, 0.05, 0.012, 4000, kind="port")
-    P = 4000
+    P = 12000
+    o = co.FlipOracle(1000.0, 2.0, 1.5, 0.05, 0.012, P, kind="port")
     pos = rng.uniform(-0.3, 2.3, (P, 2)).astype(np.float32)
     pos[:, 1] = rng.uniform(-0.3, 1.8, P).astype(np.float32)
-    pos[:300] = np.float32([0.7, 0.7]) + rng.normal(0, 1e-3, (300, 2)).astype(np.float32)   # crowd one cell
+    pos[:300] = np.float32([0.7, 0.7]) + rng.normal(0, 1e-3, (300, 2)).astype(np.float32)   # crowd one cell (sorted by a whole CTA)
     pos[300:310] = pos[300]                                                                   # exact duplicates (d==0)
+    pos[1000:6000] = np.float32([1.3, 0.4]) + rng.normal(0, 5e-4, (5000, 2)).astype(np.float32)   # > 4096 in one cell: the serial fall-back
+    pos[6000:6020] = np.float32([0.3, 1.1]) + rng.normal(0, 1e-3, (20, 2)).astype(np.float32)    # just over the in-thread limit
     o.set_num_particles(P); o.particle_pos[:] = pos.reshape(-1)
     o.particle_vel[:] = rng.normal(0, 1, 2 * P).astype(np.float32)
     s = np.ones((o.f_num_y, o.f_num_x), np.float32); s[0] = 0; s[-1] = 0; s[:, 0] = 0; s[:, -1] = 0
