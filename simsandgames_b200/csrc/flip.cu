@@ -239,7 +239,9 @@ __device__ __forceinline__ void sort_network_ascending(T (&v)[N]) {
 __global__ void __launch_bounds__(kThreads) k_fill(int np, const int* __restrict__ keys, const int* __restrict__ orig,
                                                    int* __restrict__ first, int* __restrict__ src, int* __restrict__ ids) {
 	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < np; k += gridDim.x * blockDim.x) {
-		int slot = atomicSub(first + keys[k], 1) - 1;
+		const int key = keys[k];
+		if (key < 0) continue;   // kDeadKey: a particle this rank no longer holds (sharded steps) drops out of the sort
+		int slot = atomicSub(first + key, 1) - 1;
 		src[slot] = k;
 		ids[slot] = orig[k];
 	}
@@ -872,11 +874,7 @@ __global__ void k_shard_band(int* __restrict__ vmax_bits, float dt, float gravit
 // valid rows -- is the one that survives.  (The band below is wide enough that every such particle WAS a ghost there.)
 // Kept particles within `band` rows of a boundary are copied to that neighbour as this step's ghosts.
 // Ownership is by position: a particle belongs to the rank whose slab holds its cell row; owned particles within `band` rows of
-// a slab boundary also go to that neighbour (as ghosts, or as migrants it now owns).  The three classes are compacted in
-// two passes over 256-particle chunks -- count, one scan of the chunk counts, place -- so the kept particles stay in the order
-// they had (hash-cell order from the last step): the counting sort that follows then fills and reorders with the memory
-// locality of the one-GPU step.  (Slots claimed with atomics in arrival order scrambled the chunks: k_fill 0.35 -> 0.9-1.05 ms
-// at S2, k_fixup_cells 0.49 -> 0.63 ms, profiles/r2_sharded.md.)
+// a slab boundary also go to that neighbour (as ghosts, or as migrants it now owns).
 struct ShardClass { bool own, go_down, go_up; };
 __device__ __forceinline__ ShardClass shard_class(const Geo& g, float2 p, int j0, int j1, int band, int has_down, int has_up) {
 	const int row = clampi((int)(g.inv_h * p.y), 0, g.ny - 1);
@@ -886,7 +884,9 @@ __device__ __forceinline__ ShardClass shard_class(const Geo& g, float2 p, int j0
 	c.go_up = c.own && has_up && row >= j1 - band;
 	return c;
 }
-// One WARP per chunk of kShardChunk particles (no block barriers, the chunk's loads in flight together).
+// Stable compaction of the owned particles (flip_readback_particles; boundary copies with `exchange`) in two passes over
+// 256-particle chunks -- count, one scan of the chunk counts, place -- one WARP per chunk (no block barriers, the chunk's loads
+// in flight together).  The step itself does not compact: see k_shard_key.
 constexpr int kShardChunk = 256;
 __global__ void __launch_bounds__(kThreads) k_shard_count(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
                                                           const float2* __restrict__ pos, int n_chunks, int* __restrict__ chunk_cnt /* [3][n_chunks] */) {
@@ -911,7 +911,6 @@ __global__ void __launch_bounds__(kThreads) k_shard_place(Geo g, int j0, int j1,
                                                           const float2* __restrict__ pos, const float2* __restrict__ vel, const int* __restrict__ id,
                                                           ShardPack keep, ShardPack down, ShardPack up, int n_chunks,
                                                           const int* __restrict__ chunk_cnt, const int* __restrict__ chunk_incl, int cap_send,
-                                                          int integrate, float dt, float gravity, int* __restrict__ keys, int* __restrict__ count,
                                                           int* __restrict__ counters) {
 	const int band = band_p ? *band_p : 0;
 	const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
@@ -937,25 +936,75 @@ __global__ void __launch_bounds__(kThreads) k_shard_place(Geo g, int j0, int j1,
 			// boundary copies go out as they are: their receiver integrates them
 			if (c.go_down) { const int k = at1 + __popc(m1 & lt); if (k < cap_send) { down.pos[k] = p; down.vel[k] = v; down.id[k] = gid; } }
 			if (c.go_up) { const int k = at2 + __popc(m2 & lt); if (k < cap_send) { up.pos[k] = p; up.vel[k] = v; up.id[k] = gid; } }
-			if (c.own) {
-				const int k = at0 + __popc(m0 & lt);
-				if (integrate) {
-					// the kept copy leaves integrated and keyed for the sort (the arithmetic of k_integrate_bin<true, true>): one pass
-					// over the owned particles less per step
-					integrate_one(p, v, dt, gravity);
-					const int key = hash_cell(g, p.x, p.y);
-					keys[k] = key;
-					atomicAdd(count + key, 1);
-				}
-				keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid;
-			}
+			if (c.own) { const int k = at0 + __popc(m0 & lt); keep.pos[k] = p; keep.vel[k] = v; keep.id[k] = gid; }
 			at0 += __popc(m0); at1 += __popc(m1); at2 += __popc(m2);
 		}
 	}
 }
-__global__ void k_shard_check(int* __restrict__ c, int cap_send, int max_particles) {
+// Step start of a sharded step, one pass over what the rank holds (owned particles and last step's ghosts, in hash-cell order):
+// owned particles get this step's sort key from their integrated position (the reorder pass of the sort redoes the integration,
+// as in the one-GPU step: k_integrate_bin STORE = false) and enter the hash histogram; everything else gets kDeadKey and drops
+// out of the sort, so no compaction pass is needed; owned particles within `band` rows of a slab boundary are also copied, as they
+// are, into the send buffer of that neighbour (slots claimed per warp: only the warps at a boundary have any).
+constexpr int kDeadKey = -1;
+__global__ void __launch_bounds__(kThreads) k_shard_key(Geo g, int j0, int j1, const int* __restrict__ band_p, int has_down, int has_up,
+                                                        const float2* __restrict__ pos, const float2* __restrict__ vel, const int* __restrict__ id,
+                                                        float dt, float gravity, int* __restrict__ keys, int* __restrict__ count,
+                                                        ShardPack down, ShardPack up, int cap_send, int* __restrict__ counters) {
+	const int band = *band_p;
+	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
+	int n_own = 0;
+	for (int t0 = blockIdx.x * blockDim.x; t0 < g.np; t0 += gridDim.x * blockDim.x) {   // (whole warps stay in the loop: ballots below)
+		const int t = t0 + threadIdx.x;
+		ShardClass c{false, false, false};
+		float2 p = make_float2(0.f, 0.f), v = make_float2(0.f, 0.f);
+		if (t < g.np) {
+			p = pos[t];
+			c = shard_class(g, p, j0, j1, band, has_down, has_up);
+			if (c.own) {
+				v = vel[t];
+				float2 pi = p, vi = v;
+				integrate_one(pi, vi, dt, gravity);
+				const int key = hash_cell(g, pi.x, pi.y);
+				keys[t] = key;
+				atomicAdd(count + key, 1);
+				n_own++;
+			} else {
+				keys[t] = kDeadKey;
+			}
+		}
+		const unsigned m1 = __ballot_sync(0xffffffffu, c.go_down), m2 = __ballot_sync(0xffffffffu, c.go_up);
+		if (m1) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(counters + 1, __popc(m1));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			const int k = base + __popc(m1 & lt);
+			if (c.go_down && k < cap_send) { down.pos[k] = p; down.vel[k] = v; down.id[k] = id[t]; }
+		}
+		if (m2) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(counters + 2, __popc(m2));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			const int k = base + __popc(m2 & lt);
+			if (c.go_up && k < cap_send) { up.pos[k] = p; up.vel[k] = v; up.id[k] = id[t]; }
+		}
+	}
+	// how many this rank keeps: one atomic per CTA
+	for (int o = 16; o > 0; o >>= 1) n_own += __shfl_xor_sync(0xffffffffu, n_own, o);
+	__shared__ int s_own[kThreads / 32];
+	if (lane == 0) s_own[threadIdx.x >> 5] = n_own;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int tot = 0;
+		for (int w = 0; w < kThreads / 32; w++) tot += s_own[w];
+		if (tot) atomicAdd(counters, tot);
+	}
+}
+__global__ void k_shard_check(int* __restrict__ c, int cap_send, int held, int max_particles) {
 	if (threadIdx.x != 0) return;
-	c[7] = (c[1] > cap_send || c[2] > cap_send || (long long)c[0] + c[3] + c[4] > (long long)max_particles) ? 1 : 0;
+	// [1], [2]: boundary copies leaving; [3], [4]: arriving behind the `held` particles already in the buffer
+	c[7] = (c[1] > cap_send || c[2] > cap_send || (long long)held + c[3] + c[4] > (long long)max_particles) ? 1 : 0;
 }
 
 // rest-density latch across slabs: per-rank (sum, count) over own rows, summed over ranks (flip_fluid.h:321-332)
@@ -1337,7 +1386,9 @@ void running_sum(FlipSim* f, const int* count, int n, int* first) {
 }
 
 // F2: counting sort into hash-cell order.  keys/count must already hold this step's histogram.
-int bin_from_histogram(FlipSim* f, bool integrate = false, float dt = 0.f, float gravity = 0.f) {
+// n_alive >= 0 (sharded steps): entries with kDeadKey are not placed; the reorder covers the n_alive placed ones, which is the
+// particle count from here on.
+int bin_from_histogram(FlipSim* f, bool integrate = false, float dt = 0.f, float gravity = 0.f, int n_alive = -1) {
 	Geo g = geo(f);
 	const size_t hoff = (size_t)g.pnx * g.hy0;
 	int Hc = g.pnx * (g.hy1 - g.hy0), np = g.np;
@@ -1350,18 +1401,24 @@ int bin_from_histogram(FlipSim* f, bool integrate = false, float dt = 0.f, float
 		k_fixup_cells<<<wave_grid(Hc, kThreads), kThreads, 0, f->st>>>(Hc, f->count + hoff, f->first + hoff, f->src, f->orig[n], crowd);
 		k_fixup_crowded<true><<<crowd_grid(), 256, 0, f->st>>>(crowd, f->count + hoff, f->first + hoff, f->src, f->orig[n]);
 		f->lc.n++;
-		if (f->col[0]) {
-			if (integrate) k_reorder<true, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], dt, gravity);
-			else k_reorder<true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], 0.f, 0.f);
-		} else {
-			if (integrate) k_reorder<false, true><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr, dt, gravity);
-			else k_reorder<false><<<pgrid(f), kThreads, 0, f->st>>>(g, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr, 0.f, 0.f);
+		Geo gr = g;
+		if (n_alive >= 0) gr.np = n_alive;
+		const unsigned rgrid = wave_grid((size_t)std::max(gr.np, 1), kThreads);
+		if (gr.np > 0) {
+			if (f->col[0]) {
+				if (integrate) k_reorder<true, true><<<rgrid, kThreads, 0, f->st>>>(gr, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], dt, gravity);
+				else k_reorder<true><<<rgrid, kThreads, 0, f->st>>>(gr, f->src, f->pos[c], f->vel[c], f->col[c], f->pos[n], f->vel[n], f->col[n], 0.f, 0.f);
+			} else {
+				if (integrate) k_reorder<false, true><<<rgrid, kThreads, 0, f->st>>>(gr, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr, dt, gravity);
+				else k_reorder<false><<<rgrid, kThreads, 0, f->st>>>(gr, f->src, f->pos[c], f->vel[c], nullptr, f->pos[n], f->vel[n], nullptr, 0.f, 0.f);
+			}
 		}
 		f->lc.n += 3;
 		f->cur = n;
 		f->identity = false;
 	}
 	FG_CUDA(cudaGetLastError());
+	if (n_alive >= 0) f->d.num_particles = n_alive;
 	f->bins_valid = true;
 	return FLIPGPU_OK;
 }
@@ -1673,9 +1730,9 @@ int shard_exchange_rows(FlipSim* f, void* const* fields, int n_fields, int rows)
 	return FLIPGPU_OK;
 }
 
-// Stable compaction of buffer `cur` into buffer `1 - cur`: owned particles (optionally integrated + keyed, see k_shard_place),
-// and with `exchange` the boundary copies for both neighbours into the send buffers.  Leaves the three counts in d_counters[0..2].
-int shard_compact(FlipSim* f, bool exchange, bool integrate, float dt, float gravity) {
+// Stable compaction of buffer `cur` into buffer `1 - cur`: the owned particles, and with `exchange` the boundary copies for both
+// neighbours into the send buffers.  Leaves the three counts in d_counters[0..2].
+int shard_compact(FlipSim* f, bool exchange) {
 	Geo g = geo(f);
 	if (g.np <= 0) return FLIPGPU_OK;   // (the counters were cleared by the caller)
 	const int c = f->cur, n = 1 - c;
@@ -1688,16 +1745,16 @@ int shard_compact(FlipSim* f, bool exchange, bool integrate, float dt, float gra
 	k_shard_count<<<grid, kThreads, 0, f->st>>>(g, f->j0, f->j1, band, has_down, has_up, f->pos[c], n_chunks, f->d_chunk);
 	running_sum(f, f->d_chunk, 3 * n_chunks, incl);
 	k_shard_place<<<grid, kThreads, 0, f->st>>>(g, f->j0, f->j1, band, has_down, has_up, f->pos[c], f->vel[c], f->orig[c], keep, down, up, n_chunks, f->d_chunk,
-	                                            incl, f->cap_send, integrate ? 1 : 0, dt, gravity, f->keys, f->count, f->d_counters);
+	                                            incl, f->cap_send, f->d_counters);
 	f->lc.n += 2;
 	FG_CUDA(cudaGetLastError());
 	return FLIPGPU_OK;
 }
 
 // keep what this rank owns (by position), refresh the ghosts from both neighbours
-int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters) {
+int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters, int* n_alive) {
 	Geo g = geo(f);
-	const int c = f->cur, n = 1 - c;
+	const int c = f->cur;
 	const bool has_up = f->rank + 1 < f->nranks, has_down = f->rank > 0;
 	FG_TRY(positions_will_change(f));
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
@@ -1712,7 +1769,13 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters)
 	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 8, f->d_counters + 8, 1, ncclInt, ncclMax, f->comm, f->st));
 	k_shard_band<<<1, 32, 0, f->st>>>(f->d_counters + 8, dt, gravity, f->d.h, f->d.particle_radius, sep_iters, f->d_counters + 6);
 	f->lc.n++;
-	FG_TRY(shard_compact(f, true, true, dt, gravity));
+	const int held = g.np;   // owned + last step's ghosts, in hash-cell order in buffer `cur`; arrivals are appended behind them
+	if (held > 0) {
+		ShardPack down{f->send_pos[0], f->send_vel[0], f->send_id[0]}, up{f->send_pos[1], f->send_vel[1], f->send_id[1]};
+		k_shard_key<<<pgrid(f), kThreads, 0, f->st>>>(g, f->j0, f->j1, f->d_counters + 6, has_down, has_up, f->pos[c], f->vel[c], f->orig[c], dt, gravity,
+		                                              f->keys, f->count, down, up, f->cap_send, f->d_counters);
+		f->lc.n++;
+	}
 	// tell each neighbour how many particles are coming (device-to-device ints), then read the counters once
 	if (f->nranks > 1) {
 		FG_NCCL(g_nccl.GroupStart());
@@ -1726,14 +1789,14 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters)
 		}
 		FG_NCCL(g_nccl.GroupEnd());
 	}
-	k_shard_check<<<1, 32, 0, f->st>>>(f->d_counters, f->cap_send, f->d.max_particles);
+	k_shard_check<<<1, 32, 0, f->st>>>(f->d_counters, f->cap_send, held, f->d.max_particles);
 	f->lc.n++;
 	if (f->nranks > 1) FG_NCCL(g_nccl.AllReduce(f->d_counters + 7, f->d_counters + 7, 1, ncclInt, ncclMax, f->comm, f->st));
 	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	const int n_keep = f->h_counters[0], n_down = f->h_counters[1], n_up = f->h_counters[2], from_down = f->h_counters[3], from_up = f->h_counters[4];
-	FG_CHECK(f->h_counters[7] == 0, FLIPGPU_ESTATE, "shard: a rank ran out of room in this step's particle exchange (here: %d owned + %d + %d received of %d slots, "
-	         "%d / %d boundary particles of %d send slots) -- every rank stops", n_keep, from_down, from_up, f->d.max_particles, n_down, n_up, f->cap_send);
+	FG_CHECK(f->h_counters[7] == 0, FLIPGPU_ESTATE, "shard: a rank ran out of room in this step's particle exchange (here: %d held + %d + %d received of %d slots, "
+	         "%d / %d boundary particles of %d send slots) -- every rank stops", held, from_down, from_up, f->d.max_particles, n_down, n_up, f->cap_send);
 	f->band = f->h_counters[6];
 	// (the band is the same number on every rank and min_slab_rows is too: all ranks take this exit together, none is left
 	// blocked in the NCCL group below)
@@ -1741,44 +1804,44 @@ int shard_exchange_particles(FlipSim* f, float dt, float gravity, int sep_iters)
 	         "shard: the ghost band (%d rows: fastest particle, %d separation sweeps) is wider than the thinnest slab (%d rows) -- use fewer ranks or a smaller dt",
 	         f->band, sep_iters, f->min_slab_rows);
 	FG_CHECK(n_down <= f->cap_send && n_up <= f->cap_send, FLIPGPU_ESTATE, "shard: %d/%d boundary particles exceed the send capacity %d", n_down, n_up, f->cap_send);
-	FG_CHECK((long long)n_keep + from_down + from_up <= f->d.max_particles, FLIPGPU_ESTATE, "shard: %d owned + %d + %d received exceed max_particles %d",
-	         n_keep, from_down, from_up, f->d.max_particles);
+	FG_CHECK((long long)held + from_down + from_up <= f->d.max_particles, FLIPGPU_ESTATE, "shard: %d held + %d + %d received exceed max_particles %d",
+	         held, from_down, from_up, f->d.max_particles);
 	if (f->nranks > 1) {
 		FG_NCCL(g_nccl.GroupStart());
-		int at = n_keep;
+		int at = held;
 		if (has_down) {
 			FG_NCCL(g_nccl.Send(f->send_pos[0], 2 * (size_t)n_down, ncclFloat, f->rank - 1, f->comm, f->st));
 			FG_NCCL(g_nccl.Send(f->send_vel[0], 2 * (size_t)n_down, ncclFloat, f->rank - 1, f->comm, f->st));
 			FG_NCCL(g_nccl.Send(f->send_id[0], (size_t)n_down, ncclInt, f->rank - 1, f->comm, f->st));
-			FG_NCCL(g_nccl.Recv(f->pos[n] + at, 2 * (size_t)from_down, ncclFloat, f->rank - 1, f->comm, f->st));
-			FG_NCCL(g_nccl.Recv(f->vel[n] + at, 2 * (size_t)from_down, ncclFloat, f->rank - 1, f->comm, f->st));
-			FG_NCCL(g_nccl.Recv(f->orig[n] + at, (size_t)from_down, ncclInt, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->pos[c] + at, 2 * (size_t)from_down, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->vel[c] + at, 2 * (size_t)from_down, ncclFloat, f->rank - 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->orig[c] + at, (size_t)from_down, ncclInt, f->rank - 1, f->comm, f->st));
 			at += from_down;
 		}
 		if (has_up) {
 			FG_NCCL(g_nccl.Send(f->send_pos[1], 2 * (size_t)n_up, ncclFloat, f->rank + 1, f->comm, f->st));
 			FG_NCCL(g_nccl.Send(f->send_vel[1], 2 * (size_t)n_up, ncclFloat, f->rank + 1, f->comm, f->st));
 			FG_NCCL(g_nccl.Send(f->send_id[1], (size_t)n_up, ncclInt, f->rank + 1, f->comm, f->st));
-			FG_NCCL(g_nccl.Recv(f->pos[n] + at, 2 * (size_t)from_up, ncclFloat, f->rank + 1, f->comm, f->st));
-			FG_NCCL(g_nccl.Recv(f->vel[n] + at, 2 * (size_t)from_up, ncclFloat, f->rank + 1, f->comm, f->st));
-			FG_NCCL(g_nccl.Recv(f->orig[n] + at, (size_t)from_up, ncclInt, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->pos[c] + at, 2 * (size_t)from_up, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->vel[c] + at, 2 * (size_t)from_up, ncclFloat, f->rank + 1, f->comm, f->st));
+			FG_NCCL(g_nccl.Recv(f->orig[c] + at, (size_t)from_up, ncclInt, f->rank + 1, f->comm, f->st));
 		}
 		FG_NCCL(g_nccl.GroupEnd());
 		f->exchanges++;
 	}
 	const int n_recv = from_down + from_up;
-	if (n_recv > 0) {  // the received ghosts and migrants: integrate + key + histogram like the kept ones
+	if (n_recv > 0) {  // the arrivals (ghosts, migrants): key + histogram from the integrated position like the owned ones
 		Geo gt = g;
 		gt.np = n_recv;
-		k_integrate_bin<true, true><<<wave_grid((size_t)n_recv, kThreads), kThreads, 0, f->st>>>(gt, f->pos[n] + n_keep, f->vel[n] + n_keep, dt, gravity, f->keys + n_keep, f->count);
+		k_integrate_bin<true, true, false><<<wave_grid((size_t)n_recv, kThreads), kThreads, 0, f->st>>>(gt, f->pos[c] + held, f->vel[c] + held, dt, gravity, f->keys + held, f->count);
 		f->lc.n++;
 	}
 	FG_CUDA(cudaGetLastError());
-	f->cur = n;
 	f->n_owned = n_keep;
-	f->d.num_particles = n_keep + n_recv;
+	f->d.num_particles = held + n_recv;   // what the sort reads; it leaves n_keep + n_recv (dead entries drop out)
 	f->identity = false;
 	f->bins_valid = false;
+	*n_alive = n_keep + n_recv;
 	return FLIPGPU_OK;
 }
 
@@ -1827,11 +1890,12 @@ int shard_step(FlipSim* f, const FlipStepParams* sp) {
 	// integrate_bin, post-P2G halo rows under p2g, post-solve halo rows under g2p
 	if (f->timings_on) collect_slot(f, f->ev_slot);
 	phase_mark(f, FLIP_PH_INTEGRATE_BIN);
-	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity, sp->separate_particles ? sp->num_particle_iters : 0));              // migrants change owner, ghosts are refreshed; F1 + sort keys
+	int n_alive = 0;
+	FG_TRY(shard_exchange_particles(f, sp->dt, sp->gravity, sp->separate_particles ? sp->num_particle_iters : 0, &n_alive));    // migrants change owner, ghosts are refreshed; sort keys
 	// (the exchange synchronised the stream, so the previous step -- and its copy of the rest density -- is complete on
 	// every rank: all ranks take the same branch below and issue the same NCCL calls)
 	if (!f->rest_seen && f->h_pinned[0] != 0.f) f->rest_seen = true;
-	FG_TRY(bin_from_histogram(f));                                         // owned + ghosts, integrated and keyed by the exchange
+	FG_TRY(bin_from_histogram(f, true, sp->dt, sp->gravity, n_alive));     // owned + ghosts; F1 happens in the reorder pass; what the rank no longer holds drops out
 	phase_mark(f, FLIP_PH_SEPARATE);
 	// as in the one-GPU step, the last sweep runs the collision / marking pass itself (identical results)
 	const bool fused = sp->separate_particles && sp->num_particle_iters >= 1 && f->d.num_particles > 0;
@@ -2379,7 +2443,7 @@ int flip_readback_particles(FlipSim* f, float* pos, float* vel, int* ids, int ca
 	Geo g = geo(f);
 	const int c = f->cur, n = 1 - c;
 	FG_CUDA(cudaMemsetAsync(f->d_counters, 0, 8 * sizeof(int), f->st));
-	FG_TRY(shard_compact(f, false, false, 0.f, 0.f));
+	FG_TRY(shard_compact(f, false));
 	FG_CUDA(cudaMemcpyAsync(f->h_counters, f->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, f->st));
 	FG_CUDA(cudaStreamSynchronize(f->st));
 	const int k = f->h_counters[0];
