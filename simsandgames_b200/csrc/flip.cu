@@ -436,8 +436,13 @@ __device__ __forceinline__ void mark_one(const Geo& g, float2 p, int t, int* __r
 // FUSE: the last sweep of a step also runs the collision pass, the fluid-cell marking and the key / histogram of the P2G
 // lists on the position it has just computed (the same device functions as k_collide_mark: identical results), so the
 // positions cross HBM once instead of three times and the velocity is only written where a wall or the obstacle changed it.
+// Row-walk unroll and register cap of the sweep, measured at S2 (both sweeps, ms): unroll 1 / 2 / 4 / 8 / 12 / 16 / 32 = 3.14 / 3.11 /
+// 3.22 / 2.96 / 3.05 / 2.90* / 2.98; with the kernel held to 32 registers (8 CTAs of 256 threads per SM, a 16-byte spill) unroll 8 =
+// 2.88 (*: together with the cap).  Without any minimum-blocks hint ptxas picks 32 / 39 registers, with a hint of 1 it takes 48 / 51 and
+// the sweeps cost 3.76 ms.
+constexpr int kSepUnroll = 8, kSepMinBlocks = 8;
 template <bool COLORS, bool FUSE>
-__global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
+__global__ void __launch_bounds__(kThreads, kSepMinBlocks) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
                                                        float2* __restrict__ pos_out, const float* __restrict__ col_in,
                                                        float* __restrict__ col_out, float2* __restrict__ vel, float ox, float oy,
                                                        float ovx, float ovy, float orad, int* __restrict__ cell_type,
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(kThreads) k_separate(Geo g, const int* __restr
 			for (int r = 0; r < 3; r++) {
 				const float2* __restrict__ row = pos_in + ra[r];
 				unsigned hits = 0;
-#pragma unroll 4
+#pragma unroll kSepUnroll
 				for (int i = 0; i < rn[r]; i++) {
 					float2 q = row[i];
 					float dx = q.x - p.x, dy = q.y - p.y;
@@ -719,8 +724,9 @@ __global__ void k_rest_latch(int n_partials, const float* __restrict__ partials,
 // cell_type[n2-nx] is node 1 whenever y1 == y0+1 (they differ only in the aliased last column / row, Q13).
 // STAGE: the frame pipeline's caller-order copy of the (final) positions is written from here -- the kernel is bound by
 // gather latency, not bandwidth, so the scattered 8-byte stores ride along (a separate un-permute pass costs 1.46 ms at S2).
+// (five CTAs per SM: 48 registers and an 8-byte spill instead of 60 registers -- 0.76 -> 0.70 ms at S2; six CTAs: 0.74)
 template <bool STAGE>
-__global__ void __launch_bounds__(kThreads) k_g2p(Geo g, const float2* __restrict__ pos, float2* __restrict__ vel,
+__global__ void __launch_bounds__(kThreads, 5) k_g2p(Geo g, const float2* __restrict__ pos, float2* __restrict__ vel,
                                                   const float* __restrict__ u, const float* __restrict__ v,
                                                   const float* __restrict__ prev_u, const float* __restrict__ prev_v,
                                                   const int* __restrict__ cell_type, float flip_ratio,
