@@ -436,13 +436,21 @@ __device__ __forceinline__ void mark_one(const Geo& g, float2 p, int t, int* __r
 // FUSE: the last sweep of a step also runs the collision pass, the fluid-cell marking and the key / histogram of the P2G
 // lists on the position it has just computed (the same device functions as k_collide_mark: identical results), so the
 // positions cross HBM once instead of three times and the velocity is only written where a wall or the obstacle changed it.
-// Row-walk unroll and register cap of the sweep, measured at S2 (both sweeps, ms): unroll 1 / 2 / 4 / 8 / 12 / 16 / 32 = 3.14 / 3.11 /
-// 3.22 / 2.96 / 3.05 / 2.90* / 2.98; with the kernel held to 32 registers (8 CTAs of 256 threads per SM, a 16-byte spill) unroll 8 =
-// 2.88 (*: together with the cap).  Without any minimum-blocks hint ptxas picks 32 / 39 registers, with a hint of 1 it takes 48 / 51 and
-// the sweeps cost 3.76 ms.
-constexpr int kSepUnroll = 8, kSepMinBlocks = 8;
+// Row-walk unroll and register cap of the sweep, measured at S2 (both sweeps, ms) on the benchmark's near-lattice dam-break state:
+// unroll 1 / 2 / 4 / 8 / 12 / 16 / 32 = 3.14 / 3.11 / 3.22 / 2.96 / 3.05 / 2.90* / 2.98; with the kernel held to 32 registers (8 CTAs of
+// 256 threads per SM, a 16-byte spill) unroll 2 / 4 / 8 = 3.08 / 3.19 / 2.88 (*: together with the cap).  Without any minimum-blocks
+// hint ptxas picks 32 / 39 registers, with a hint of 1 it takes 48 / 51 and the sweeps cost 3.76 ms.  The choice is state dependent:
+// on the developed-flow state of bench.py (crowded cells, ragged rows) unroll 8 costs 4.32 ms against 4.02 (unroll 4) / 4.04 (unroll 2)
+// under the same cap -- the longer unrolled groups run more masked-off candidates; the defaults follow the headline configuration.
+#ifndef SEP_UNROLL
+#define SEP_UNROLL 8
+#endif
+#ifndef SEP_MINB
+#define SEP_MINB 8
+#endif
+constexpr int kSepUnroll = SEP_UNROLL, kSepMinBlocks = SEP_MINB;
 template <bool COLORS, bool FUSE>
-__global__ void __launch_bounds__(kThreads, kSepMinBlocks) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
+__global__ void __launch_bounds__(kThreads, kSepMinBlocks > 0 ? kSepMinBlocks : 1) k_separate(Geo g, const int* __restrict__ first, const float2* __restrict__ pos_in,
                                                        float2* __restrict__ pos_out, const float* __restrict__ col_in,
                                                        float* __restrict__ col_out, float2* __restrict__ vel, float ox, float oy,
                                                        float ovx, float ovy, float orad, int* __restrict__ cell_type,
