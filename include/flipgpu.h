@@ -239,7 +239,9 @@ int fluid3d_get_launch_count(Fluid3DSim* sim, long long* launches);
  * communication-avoiding deep halo (halo_rows rows every halo_rows-1 colour passes).  Positions stay in GLOBAL
  * coordinates and particles carry their global caller index, so with the rest density given the result is
  * bit-identical to the one-GPU FLIP_SOLVER_RED_BLACK run (tests/test_gpu_multi.py).  params->max_particles is the
- * per-rank capacity (owned + ghosts).  Only FLIP_SOLVER_RED_BLACK, update_colors = 0. */
+ * per-rank capacity: the owned particles plus TWO steps' ghosts (a step's arrivals are appended behind what the rank
+ * already holds; what it no longer holds drops out in that step's sort).  Running out of room is an error on every rank
+ * (FLIPGPU_ESTATE), never a silent drop.  Only FLIP_SOLVER_RED_BLACK, update_colors = 0. */
 int flip_create_sharded(const FlipParams* params, int global_particles, int rank, int nranks, const void* unique_id128, FlipSim** out);
 /* same with caller-chosen slabs: row_starts[0..nranks] ascending from 0 to f_num_y, rank r owns rows [row_starts[r], row_starts[r+1])
  * (every slab at least halo_rows+1 rows); NULL = equal slabs.  Lets the caller balance a scene whose liquid does not fill the
